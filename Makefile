@@ -1,0 +1,31 @@
+# Build libnvcomp.so (B200 / sm_100a only) and the CPU oracle.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Invcomp_b200/csrc
+SRC_DIR   := nvcomp_b200/csrc
+BUILD_DIR := build
+LIB       := nvcomp_b200/lib/libnvcomp.so
+SRCS      := $(wildcard $(SRC_DIR)/*.cu)
+OBJS      := $(patsubst $(SRC_DIR)/%.cu,$(BUILD_DIR)/%.o,$(SRCS))
+HDRS      := $(wildcard $(SRC_DIR)/*.cuh) $(wildcard $(SRC_DIR)/*.h) $(wildcard include/nvcomp/*.h) $(wildcard include/nvcomp/*.hpp) $(wildcard include/*.hpp)
+
+ORACLE_SRCS := $(wildcard oracle/*.c)
+ORACLE_LIB  := oracle/liboracle.so
+
+all: $(LIB) $(ORACLE_LIB)
+
+$(BUILD_DIR)/%.o: $(SRC_DIR)/%.cu $(HDRS)
+	@mkdir -p $(BUILD_DIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD_DIR)/$*.ptxas.log || (cat $(BUILD_DIR)/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	@mkdir -p nvcomp_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+
+$(ORACLE_LIB): $(ORACLE_SRCS) $(wildcard oracle/*.h)
+	gcc -O3 -march=x86-64-v2 -fPIC -shared -Wall -o $@ $(ORACLE_SRCS)
+
+clean:
+	rm -rf $(BUILD_DIR) $(LIB) $(ORACLE_LIB)
+
+.PHONY: all clean

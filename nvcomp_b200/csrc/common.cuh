@@ -1,0 +1,213 @@
+// common.cuh -- shared device/host helpers for the B200-native batched codecs.
+//
+// Everything here is internal to libnvcomp.so (sm_100a only).  The public
+// boundary is include/nvcomp/*.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "nvcomp/shared_types.h"
+
+namespace b200 {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNumSMsB200 = 148;
+
+// Bytes at the head of every decompress/compress workspace reserved for the
+// persistent chunk scheduler (one 64-bit ticket counter per launch, padded).
+constexpr size_t kSchedBytes = 256;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---------------------------------------------------------------------------
+// Persistent chunk scheduler: every warp (or CTA) pulls the next chunk index
+// from a global ticket counter, so thousands of unequal chunks keep all 148
+// SMs busy until the batch drains (no static wave quantisation).
+// ---------------------------------------------------------------------------
+struct WarpTicket {
+  unsigned long long* counter;  // nullptr -> static grid-stride assignment
+  size_t static_next;
+  size_t static_stride;
+  __device__ __forceinline__ WarpTicket(unsigned long long* c, size_t warp_global, size_t warps_total)
+      : counter(c), static_next(warp_global), static_stride(warps_total) {}
+  __device__ __forceinline__ size_t next(int lane) {
+    if (counter == nullptr) {
+      size_t r = static_next;
+      static_next += static_stride;
+      return r;
+    }
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1ull);
+    return (size_t)__shfl_sync(kFull, t, 0);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Global-memory access helpers.
+// ---------------------------------------------------------------------------
+// Read-only, streaming (compressed input is read once): bypass L1 allocation.
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// Streaming store: decompressed output is written once, never re-read by this
+// kernel beyond the match window, so do not let it thrash L1.
+__device__ __forceinline__ void st_v4(uint4* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_v4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+// Unaligned little-endian loads from byte pointers (no alignment assumed).
+__device__ __forceinline__ uint32_t load_u16(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+}
+__device__ __forceinline__ uint32_t load_u32(const uint8_t* p) {
+  uintptr_t a = (uintptr_t)p;
+  const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+  uint32_t sh = (uint32_t)(a & 3) * 8;
+  uint32_t lo = w[0];
+  if (sh == 0) return lo;
+  uint32_t hi = w[1];
+  return __funnelshift_r(lo, hi, sh);
+}
+
+// Select 4 consecutive words starting at word `ws` (0..3) of an 8-word window
+// and byte-shift by `bs` bits; ws/bs are warp-uniform so the switch does not
+// diverge.  This is the funnel-shift realignment that lets an arbitrarily
+// aligned source feed 16-byte aligned destination stores.
+__device__ __forceinline__ uint4 realign16(const uint4& a, const uint4& b, uint32_t ws, uint32_t bs) {
+  uint32_t w0, w1, w2, w3, w4;
+  switch (ws) {
+    case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+    case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+    case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+    default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+  }
+  uint4 r;
+  r.x = __funnelshift_r(w0, w1, bs);
+  r.y = __funnelshift_r(w1, w2, bs);
+  r.z = __funnelshift_r(w2, w3, bs);
+  r.w = __funnelshift_r(w3, w4, bs);
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative copy of n bytes, src and dst do not overlap within the span
+// being copied.  Long spans move as 16-byte vectors: destination stores are
+// 16-byte aligned, the source is re-aligned with funnel shifts.  RO selects the
+// non-coherent path for sources that this kernel never writes (compressed
+// input); sources inside the output buffer must use coherent loads.
+// Reads may touch up to 15 bytes before/after [src, src+n) but never leave the
+// 16-byte granules that contain valid bytes (so they cannot fault).
+// ---------------------------------------------------------------------------
+template <bool RO>
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+  if (n < 96) {
+    for (uint32_t i = lane; i < n; i += kWarp) dst[i] = src[i];
+    return;
+  }
+  uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15)) & 15u;
+  if ((uint32_t)lane < head) dst[lane] = src[lane];
+  dst += head; src += head; n -= head;
+  const uint32_t nvec = n >> 4;
+  const uint32_t mis = (uint32_t)((uintptr_t)src & 15);
+  const uint4* s16 = (const uint4*)(src - mis);
+  uint4* d16 = (uint4*)dst;
+  if (mis == 0) {
+    for (uint32_t v = lane; v < nvec; v += kWarp) {
+      uint4 a = RO ? ld_nc_v4(s16 + v) : ld_v4(s16 + v);
+      st_v4(d16 + v, a);
+    }
+  } else {
+    const uint32_t ws = mis >> 2, bs = (mis & 3) * 8;
+    for (uint32_t v = lane; v < nvec; v += kWarp) {
+      uint4 a = RO ? ld_nc_v4(s16 + v) : ld_v4(s16 + v);
+      uint4 b = RO ? ld_nc_v4(s16 + v + 1) : ld_v4(s16 + v + 1);
+      st_v4(d16 + v, realign16(a, b, ws, bs));
+    }
+  }
+  const uint32_t done = nvec << 4;
+  const uint32_t tail = n - done;
+  if ((uint32_t)lane < tail) dst[done + lane] = src[done + lane];
+}
+
+// ---------------------------------------------------------------------------
+// LZ77 match copy: dst[0..len) = dst[-off .. -off+len) with the usual
+// byte-serial semantics (off may be smaller than len: the pattern repeats).
+// All bytes before dst are already globally visible to the warp (caller did a
+// __syncwarp after the last stores).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void warp_match_copy(uint8_t* dst, uint32_t off, uint32_t len, int lane) {
+  const uint8_t* src = dst - off;
+  if (off >= len) {
+    warp_copy<false>(dst, src, len, lane);
+    return;
+  }
+  if (off < 32) {
+    // Every output byte j equals src[j mod off]; all of src lies before dst, so
+    // the lanes are independent: no intra-copy hazard, no sync between rounds.
+    const bool pow2 = (off & (off - 1)) == 0;   // off in {1,2,4,8,16}
+    if (pow2 && len >= 64) {
+      // Periodic run (typed RLE): the period divides 16, so every 16-byte
+      // aligned vector of the run is identical.  Materialise the first aligned
+      // vector bytewise, then broadcast it with 16-byte stores.
+      uint32_t head = ((16u - (uint32_t)((uintptr_t)dst & 15)) & 15u) + 16u;  // 16..31
+      if ((uint32_t)lane < head) dst[lane] = src[lane & (off - 1)];
+      __syncwarp();
+      uint8_t* a = dst + head - 16;
+      uint4 pat = ld_v4((const uint4*)a);
+      uint32_t nvec = (len - head) >> 4;
+      uint4* d16 = (uint4*)(a + 16);
+      for (uint32_t v = lane; v < nvec; v += kWarp) st_v4(d16 + v, pat);
+      uint32_t done = head + (nvec << 4);
+      uint32_t j = done + lane;
+      if (j < len) dst[j] = src[j & (off - 1)];
+      return;
+    }
+    uint32_t r = (uint32_t)lane % off;
+    const uint32_t step = 32u % off;
+    for (uint32_t j = lane; j < len; j += kWarp) {
+      dst[j] = src[r];
+      r += step;
+      if (r >= off) r -= off;
+    }
+    return;
+  }
+  // off >= 32, overlapping: copy in doubling spans, each span's source is
+  // complete before the span starts (span <= k*off).
+  uint32_t done = 0, span = off;
+  while (done < len) {
+    uint32_t n = min(span, len - done);
+    warp_copy<false>(dst + done, dst + done - span, n, lane);
+    done += n;
+    span <<= 1;
+    __syncwarp();
+  }
+}
+
+// Host-side launch helper: number of CTAs for a persistent kernel.
+inline int persistent_grid(int ctas_per_sm, size_t work_items, int work_per_cta) {
+  size_t need = (work_items + (size_t)work_per_cta - 1) / (size_t)work_per_cta;
+  size_t cap = (size_t)kNumSMsB200 * (size_t)ctas_per_sm;
+  size_t g = need < cap ? need : cap;
+  return (int)(g == 0 ? 1 : g);
+}
+
+#define B200_CUDA_TRY(expr)                                  \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return nvcompErrorCudaError;      \
+  } while (0)
+
+}  // namespace b200

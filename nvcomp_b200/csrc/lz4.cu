@@ -1,0 +1,273 @@
+// lz4.cu -- batched LZ4 block codec for B200 (sm_100a) + its C ABI.
+//
+// Replaces the closed nvcompBatchedLZ4* entry points (include/nvcomp/lz4.h).
+// Wire format: LZ4 block format, one block per chunk, interoperable with
+// liblz4 1.9.4 in both directions (reference examples/lz4_cpu_compression.cu,
+// examples/lz4_cpu_decompression.cu).
+//
+// Decode: one warp owns one chunk; chunks are handed out by a persistent
+// ticket scheduler.  Token fields are parsed warp-uniformly; literal runs and
+// match runs move as 16-byte vectors (common.cuh: warp_copy / warp_match_copy).
+#include "common.cuh"
+#include "lz77_compress.cuh"
+#include "nvcomp/lz4.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------
+// Length-extension bytes (the 255,255,...,x tail of a 15 nibble): 32 bytes are
+// examined per round with a ballot instead of a serial byte walk.
+// Returns false on input overrun.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool lz4_read_ext(const uint8_t* __restrict__ in, uint32_t in_n,
+                                             uint32_t& ip, uint32_t& len, int lane) {
+  while (true) {
+    const uint32_t q = ip + lane;
+    const uint32_t b = (q < in_n) ? in[q] : 0u;   // 0 terminates: overrun detected below
+    const unsigned stop = __ballot_sync(kFull, b != 255u);
+    if (stop == 0) { len += 255u * 32u; ip += 32; continue; }
+    const int k = __ffs(stop) - 1;
+    len += 255u * (uint32_t)k + __shfl_sync(kFull, b, k);
+    ip += k + 1;
+    return ip <= in_n;
+  }
+}
+
+// Decode one LZ4 block.  kWrite=false only walks the tokens (size query).
+// Returns true on success; *produced receives the decompressed size.
+template <bool kWrite>
+__device__ __forceinline__ bool lz4_decode_chunk(const uint8_t* __restrict__ in, uint32_t in_n,
+                                                 uint8_t* out, uint64_t out_cap,
+                                                 uint32_t* produced, int lane) {
+  uint32_t ip = 0;
+  uint64_t op = 0;
+  if (in_n == 0) { *produced = 0; return true; }
+  while (true) {
+    if (ip >= in_n) return false;
+    const uint32_t tok = in[ip++];
+    uint32_t ll = tok >> 4;
+    if (ll == 15) { if (!lz4_read_ext(in, in_n, ip, ll, lane)) return false; }
+    if (ll > in_n - ip) return false;
+    if (kWrite) {
+      if ((uint64_t)ll > out_cap - op) return false;
+      if (ll) warp_copy<true>(out + op, in + ip, ll, lane);
+    }
+    ip += ll; op += ll;
+    if (ip >= in_n) break;                 // last sequence carries literals only
+    if (in_n - ip < 2) return false;
+    const uint32_t off = load_u16(in + ip);
+    ip += 2;
+    uint32_t ml = tok & 15u;
+    if (ml == 15) { if (!lz4_read_ext(in, in_n, ip, ml, lane)) return false; }
+    ml += 4;
+    if (off == 0 || (uint64_t)off > op) return false;
+    if (kWrite) {
+      if ((uint64_t)ml > out_cap - op) return false;
+      __syncwarp();                        // prior stores visible to all lanes
+      warp_match_copy(out + op, off, ml, lane);
+      __syncwarp();
+    }
+    op += ml;
+    if (op > 0xffffffffull) return false;
+  }
+  *produced = (uint32_t)op;
+  return true;
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(128)
+lz4_decompress_kernel(const void* const* __restrict__ comp_ptrs,
+                      const size_t* __restrict__ comp_bytes,
+                      const size_t* __restrict__ out_caps,
+                      size_t* actual_bytes, size_t batch,
+                      void* const* __restrict__ out_ptrs,
+                      nvcompStatus_t* statuses,
+                      unsigned long long* ticket) {
+  const int lane = lane_id();
+  const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+  WarpTicket sched(ticket, warp_global, warps_total);
+  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
+    const size_t in_n64 = comp_bytes[c];
+    uint8_t* out = kWrite ? (uint8_t*)out_ptrs[c] : nullptr;
+    const uint64_t cap = kWrite ? (uint64_t)out_caps[c] : ~0ull;
+    uint32_t produced = 0;
+    bool ok = in_n64 <= 0xffffffffull;
+    if (ok) ok = lz4_decode_chunk<kWrite>(in, (uint32_t)in_n64, out, cap, &produced, lane);
+    if (lane == 0) {
+      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
+      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Compression
+// ---------------------------------------------------------------------------
+struct Lz4Emitter {
+  uint8_t* out;
+  uint32_t op;
+
+  __device__ __forceinline__ void ext(uint32_t rem, int lane) {   // rem = len - 15
+    const uint32_t nb = rem / 255u + 1u;
+    for (uint32_t i = lane; i < nb; i += kWarp)
+      out[op + i] = (i + 1 < nb) ? (uint8_t)255 : (uint8_t)(rem - 255u * (nb - 1));
+    op += nb;
+  }
+  __device__ __forceinline__ void sequence(const uint8_t* lit, uint32_t ll, uint32_t off,
+                                           uint32_t ml, int lane) {
+    const uint32_t mlc = ml - 4;
+    if (lane == 0) out[op] = (uint8_t)((min(ll, 15u) << 4) | min(mlc, 15u));
+    op += 1;
+    if (ll >= 15) ext(ll - 15, lane);
+    if (ll) warp_copy<true>(out + op, lit, ll, lane);
+    op += ll;
+    if (lane == 0) { out[op] = (uint8_t)(off & 255u); out[op + 1] = (uint8_t)(off >> 8); }
+    op += 2;
+    if (mlc >= 15) ext(mlc - 15, lane);
+  }
+  __device__ __forceinline__ void finish(const uint8_t* lit, uint32_t ll, int lane) {
+    if (lane == 0) out[op] = (uint8_t)(min(ll, 15u) << 4);
+    op += 1;
+    if (ll >= 15) ext(ll - 15, lane);
+    if (ll) warp_copy<true>(out + op, lit, ll, lane);
+    op += ll;
+  }
+};
+
+constexpr int kCompWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(kCompWarpsPerCta * 32)
+lz4_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* __restrict__ in_bytes,
+                    size_t batch, void* const* __restrict__ out_ptrs, size_t* out_bytes,
+                    uint32_t step, unsigned long long* ticket) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = lane_id();
+  const int w = threadIdx.x >> 5;
+  uint16_t* table = (uint16_t*)(smem + (size_t)w * kHashBytesPerWarp);
+  const size_t warp_global = (size_t)blockIdx.x * kCompWarpsPerCta + w;
+  const size_t warps_total = (size_t)gridDim.x * kCompWarpsPerCta;
+  WarpTicket sched(ticket, warp_global, warps_total);
+  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+    const uint8_t* in = (const uint8_t*)in_ptrs[c];
+    const uint32_t n = (uint32_t)in_bytes[c];
+    Lz4Emitter em{(uint8_t*)out_ptrs[c], 0};
+    // LZ4 end-of-block rules: last 5 bytes are literals, the last match starts
+    // at least 12 bytes before the end (reference CHANGELOG.md:195).
+    lz77_compress_chunk(in, n, em, table, step, 5u, 12u, lane);
+    if (lane == 0) out_bytes[c] = em.op;
+    __syncwarp();
+  }
+}
+
+inline uint32_t lz4_step_for(nvcompType_t t, bool* ok) {
+  *ok = true;
+  switch (t) {
+    case NVCOMP_TYPE_CHAR: case NVCOMP_TYPE_UCHAR: case NVCOMP_TYPE_BITS: return 1;
+    case NVCOMP_TYPE_SHORT: case NVCOMP_TYPE_USHORT: return 2;
+    case NVCOMP_TYPE_INT: case NVCOMP_TYPE_UINT: return 4;
+    default: *ok = false; return 1;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+nvcompStatus_t nvcompBatchedLZ4CompressGetTempSize(
+    size_t, size_t max_chunk, nvcompBatchedLZ4Opts_t opts, size_t* temp_bytes) {
+  bool ok; lz4_step_for(opts.data_type, &ok);
+  if (!temp_bytes || !ok) return nvcompErrorInvalidValue;
+  if (max_chunk > nvcompLZ4CompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
+  *temp_bytes = kSchedBytes;
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedLZ4CompressGetTempSizeEx(
+    size_t batch, size_t max_chunk, nvcompBatchedLZ4Opts_t opts, size_t* temp_bytes, const size_t) {
+  return nvcompBatchedLZ4CompressGetTempSize(batch, max_chunk, opts, temp_bytes);
+}
+
+nvcompStatus_t nvcompBatchedLZ4CompressGetMaxOutputChunkSize(
+    size_t max_chunk, nvcompBatchedLZ4Opts_t, size_t* max_compressed_bytes) {
+  if (!max_compressed_bytes) return nvcompErrorInvalidValue;
+  if (max_chunk > nvcompLZ4CompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
+  // LZ4_compressBound: n + n/255 + 16
+  *max_compressed_bytes = max_chunk + max_chunk / 255 + 16;
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedLZ4CompressAsync(
+    const void* const* in_ptrs, const size_t* in_bytes, size_t max_chunk, size_t batch,
+    void* temp, size_t temp_bytes, void* const* out_ptrs, size_t* out_bytes,
+    nvcompBatchedLZ4Opts_t opts, cudaStream_t stream) {
+  bool ok; const uint32_t step = lz4_step_for(opts.data_type, &ok);
+  if (!ok) return nvcompErrorInvalidValue;
+  if (max_chunk > nvcompLZ4CompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
+  if (batch == 0) return nvcompSuccess;
+  if (!in_ptrs || !in_bytes || !out_ptrs || !out_bytes) return nvcompErrorInvalidValue;
+  unsigned long long* ticket = nullptr;
+  if (temp && temp_bytes >= kSchedBytes) {
+    ticket = (unsigned long long*)temp;
+    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+  }
+  const size_t smem = (size_t)kCompWarpsPerCta * kHashBytesPerWarp;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(lz4_compress_kernel,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = persistent_grid(3, batch, kCompWarpsPerCta);
+  lz4_compress_kernel<<<grid, kCompWarpsPerCta * 32, smem, stream>>>(
+      in_ptrs, in_bytes, batch, out_ptrs, out_bytes, step, ticket);
+  B200_CUDA_TRY(cudaGetLastError());
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedLZ4DecompressGetTempSize(
+    size_t, size_t, size_t* temp_bytes) {
+  if (!temp_bytes) return nvcompErrorInvalidValue;
+  *temp_bytes = kSchedBytes;
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedLZ4DecompressGetTempSizeEx(
+    size_t n, size_t m, size_t* temp_bytes, size_t) {
+  return nvcompBatchedLZ4DecompressGetTempSize(n, m, temp_bytes);
+}
+
+nvcompStatus_t nvcompBatchedLZ4GetDecompressSizeAsync(
+    const void* const* comp_ptrs, const size_t* comp_bytes, size_t* out_sizes,
+    size_t batch, cudaStream_t stream) {
+  if (batch == 0) return nvcompSuccess;
+  if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
+  const int grid = persistent_grid(8, batch, 4);
+  lz4_decompress_kernel<false><<<grid, 128, 0, stream>>>(
+      comp_ptrs, comp_bytes, nullptr, out_sizes, batch, nullptr, nullptr, nullptr);
+  B200_CUDA_TRY(cudaGetLastError());
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
+    const void* const* comp_ptrs, const size_t* comp_bytes, const size_t* out_caps,
+    size_t* actual_bytes, size_t batch, void* const temp, size_t temp_bytes,
+    void* const* out_ptrs, nvcompStatus_t* statuses, cudaStream_t stream) {
+  if (batch == 0) return nvcompSuccess;
+  if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
+  unsigned long long* ticket = nullptr;
+  if (temp && temp_bytes >= kSchedBytes) {
+    ticket = (unsigned long long*)temp;
+    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+  }
+  const int grid = persistent_grid(8, batch, 4);
+  lz4_decompress_kernel<true><<<grid, 128, 0, stream>>>(
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+  B200_CUDA_TRY(cudaGetLastError());
+  return nvcompSuccess;
+}
+
+}  // extern "C"

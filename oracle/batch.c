@@ -1,0 +1,67 @@
+/*
+ * batch.c -- pthread batch runner used as the CPU baseline (test infrastructure;
+ * see oracle.h).  One contiguous chunk range per thread, wall-clock timed.
+ */
+#define _GNU_SOURCE
+#include "oracle.h"
+#include <pthread.h>
+#include <time.h>
+
+long oracle_cascaded_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) __attribute__((weak));
+long oracle_bitcomp_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) __attribute__((weak));
+long oracle_ans_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) __attribute__((weak));
+
+typedef struct {
+  int codec;
+  const uint8_t* comp;
+  const size_t* off;
+  const size_t* len;
+  size_t begin, end;
+  uint8_t* out;
+  size_t stride;
+  size_t* out_len;
+  int failed;
+} job_t;
+
+static void* worker(void* p)
+{
+  job_t* j = (job_t*)p;
+  for (size_t i = j->begin; i < j->end; ++i) {
+    long r = -1;
+    const uint8_t* s = j->comp + j->off[i];
+    uint8_t* d = j->out + i * j->stride;
+    switch (j->codec) {
+    case ORACLE_LZ4: r = oracle_lz4_decompress(s, j->len[i], d, j->stride); break;
+    case ORACLE_SNAPPY: r = oracle_snappy_decompress(s, j->len[i], d, j->stride); break;
+    case ORACLE_CASCADED: if (oracle_cascaded_decompress) r = oracle_cascaded_decompress(s, j->len[i], d, j->stride); break;
+    case ORACLE_BITCOMP: if (oracle_bitcomp_decompress) r = oracle_bitcomp_decompress(s, j->len[i], d, j->stride); break;
+    case ORACLE_ANS: if (oracle_ans_decompress) r = oracle_ans_decompress(s, j->len[i], d, j->stride); break;
+    default: break;
+    }
+    if (r < 0) { j->failed = 1; r = 0; }
+    if (j->out_len) j->out_len[i] = (size_t)r;
+  }
+  return 0;
+}
+
+double oracle_batch_decompress(int codec, const uint8_t* comp, const size_t* comp_off,
+                               const size_t* comp_len, size_t count, uint8_t* out,
+                               size_t out_stride, size_t* out_len, int nthreads)
+{
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  job_t jobs[256];
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < nthreads; ++t) {
+    jobs[t] = (job_t){codec, comp, comp_off, comp_len, count * t / nthreads, count * (t + 1) / nthreads,
+                      out, out_stride, out_len, 0};
+    pthread_create(&th[t], 0, worker, &jobs[t]);
+  }
+  int failed = 0;
+  for (int t = 0; t < nthreads; ++t) { pthread_join(th[t], 0); failed |= jobs[t].failed; }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  double s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return failed ? -s : s;
+}
