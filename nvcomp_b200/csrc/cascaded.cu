@@ -1,0 +1,638 @@
+// cascaded.cu -- batched Cascaded codec (RLE x n, delta x m, frame-of-reference
+// bit-packing) for B200 (sm_100a) + its C ABI.
+//
+// Replaces the closed nvcompBatchedCascaded* entry points
+// (include/nvcomp/cascaded.h; reference benchmarks/benchmark_cascaded_chunked.cu:138-142).
+// Algorithm: reference doc/cascaded_overview.md:7-42 -- RLE and delta layers are
+// interleaved (values out of RLE i feed delta i), then every resulting stream
+// (all run-length streams and the final value stream) is bit-packed against its
+// minimum.  The reference bitstream is undocumented, so this is our own:
+//
+// Chunk stream (8-byte aligned):
+//   u32 magic 'CSC1' | u8 type | u8 num_RLEs | u8 num_deltas | u8 use_bp
+//   u32 uncompressed_bytes, u32 part_bytes, u32 num_parts
+//   u32 part_off[num_parts+1]      byte offsets of each partition payload (8-aligned)
+//   partition payloads
+// Partition payload (independent, opts.chunk_size bytes of input each):
+//   u64 first[num_deltas]          first value removed by delta layer i
+//   stream runs_0 .. runs_{R-1}, stream vals
+// Stream: u32 count, u32 bits, u64 min, then ceil(count*bits/64) u64 words;
+//   value k = min + bits [k*bits, (k+1)*bits) (little-endian bit order).
+//   use_bp = 0 forces bits = 8*sizeof(T) (runs: 16), min = 0.
+//
+// Decode: one CTA per chunk (persistent ticket), one warp per partition; all
+// layers run out of shared memory (unpack -> warp-tile prefix sums -> run
+// expansion by head-flag scatter + max-scan) and the partition is written once
+// with coalesced stores.
+#include "common.cuh"
+#include "nvcomp/cascaded.h"
+
+namespace b200 {
+
+constexpr uint32_t kCascMagic = 0x31435343u;  // "CSC1"
+constexpr int kCascWarps = 4;
+constexpr uint32_t kCascFastPart = 4096;      // partitions up to this size: one warp each
+constexpr uint32_t kCascMaxPart = 16384;
+// per-warp shared memory: A, B value buffers (P bytes each) + run/idx u16 arrays
+// sized for 1-byte elements (2*P each) = 6*P.
+constexpr uint32_t kCascSmemPerWarp = 6 * kCascFastPart;
+constexpr uint32_t kCascSmem = kCascWarps * kCascSmemPerWarp;   // 96 KB = 6 * kCascMaxPart
+
+__host__ __device__ inline uint32_t casc_type_size(int t) {
+  switch (t) {
+    case NVCOMP_TYPE_CHAR: case NVCOMP_TYPE_UCHAR: return 1;
+    case NVCOMP_TYPE_SHORT: case NVCOMP_TYPE_USHORT: return 2;
+    case NVCOMP_TYPE_INT: case NVCOMP_TYPE_UINT: return 4;
+    case NVCOMP_TYPE_LONGLONG: case NVCOMP_TYPE_ULONGLONG: return 8;
+    default: return 0;
+  }
+}
+__host__ __device__ inline bool casc_type_signed(int t) {
+  return t == NVCOMP_TYPE_CHAR || t == NVCOMP_TYPE_SHORT || t == NVCOMP_TYPE_INT || t == NVCOMP_TYPE_LONGLONG;
+}
+
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = __shfl_up_sync(kFull, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(kFull, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_max_u32(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(kFull, v, d);
+    if (lane >= d) v = max(v, o);
+  }
+  return v;
+}
+
+// typed smem element access with values carried as u64 (wrapping arithmetic)
+template <int TS> struct Elem;
+template <> struct Elem<1> { using T = uint8_t; };
+template <> struct Elem<2> { using T = uint16_t; };
+template <> struct Elem<4> { using T = uint32_t; };
+template <> struct Elem<8> { using T = uint64_t; };
+
+template <int TS> __device__ __forceinline__ uint64_t sext(uint64_t v) {
+  if (TS == 8) return v;
+  const int sh = 64 - 8 * TS;
+  return (uint64_t)(((int64_t)(v << sh)) >> sh);
+}
+
+// ----- packed stream reader ---------------------------------------------------
+struct StreamHdr { uint32_t count, bits; uint64_t minv; };
+
+__device__ __forceinline__ uint64_t unpack_at(const uint64_t* __restrict__ words, uint32_t k,
+                                              uint32_t bits, uint64_t minv) {
+  if (bits == 0) return minv;
+  const uint64_t bitpos = (uint64_t)k * bits;
+  const uint32_t w = (uint32_t)(bitpos >> 6), s = (uint32_t)(bitpos & 63);
+  uint64_t v = words[w] >> s;
+  if (s + bits > 64) v |= words[w + 1] << (64 - s);
+  if (bits < 64) v &= ((1ull << bits) - 1ull);
+  return v + minv;
+}
+
+__host__ __device__ inline uint32_t stream_bytes(uint32_t count, uint32_t bits) {
+  return 16u + 8u * (uint32_t)(((uint64_t)count * bits + 63) / 64);
+}
+
+// ---------------------------------------------------------------------------
+// Decode one partition with one warp.  `n_out` elements expected.
+// sm layout (per warp): A [P] | B [P] | runs u16[P] | idx u16[P]
+// Returns false on a malformed partition.
+// ---------------------------------------------------------------------------
+template <int TS>
+__device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t payload_bytes,
+                                 uint8_t* out, uint32_t n_out, int R, int D,
+                                 uint8_t* sm, uint32_t P, int lane) {
+  using T = typename Elem<TS>::T;
+  T* bufA = (T*)sm;
+  T* bufB = (T*)(sm + P);
+  uint16_t* runs = (uint16_t*)(sm + 2 * P);
+  uint16_t* idx = (uint16_t*)(sm + 4 * P);
+  const uint32_t cap = P / TS;
+  if (n_out > cap) return false;
+
+  // walk stream headers
+  const uint32_t firsts_bytes = 8u * (uint32_t)D + ((4u * (uint32_t)D + 7u) & ~7u);
+  if (payload_bytes < firsts_bytes) return false;
+  const uint64_t* firsts = (const uint64_t*)payload;
+  const uint32_t* cin = (const uint32_t*)(payload + 8u * (uint32_t)D);   // element count entering delta i
+  uint32_t off = firsts_bytes;
+  uint32_t run_off[8];
+  StreamHdr run_hdr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < R) {
+      if (off + 16 > payload_bytes) return false;
+      const uint32_t* h = (const uint32_t*)(payload + off);
+      run_hdr[i].count = h[0]; run_hdr[i].bits = h[1];
+      run_hdr[i].minv = *(const uint64_t*)(payload + off + 8);
+      if (run_hdr[i].bits > 64 || run_hdr[i].count > cap) return false;
+      run_off[i] = off + 16;
+      off += stream_bytes(run_hdr[i].count, run_hdr[i].bits);
+      if (off > payload_bytes) return false;
+    }
+  }
+  if (off + 16 > payload_bytes) return false;
+  StreamHdr vh;
+  {
+    const uint32_t* h = (const uint32_t*)(payload + off);
+    vh.count = h[0]; vh.bits = h[1];
+    vh.minv = *(const uint64_t*)(payload + off + 8);
+  }
+  if (vh.bits > 64 || vh.count > cap) return false;
+  const uint64_t* vwords = (const uint64_t*)(payload + off + 16);
+  if (off + stream_bytes(vh.count, vh.bits) > payload_bytes) return false;
+
+  // unpack the final value stream into A
+  uint32_t count = vh.count;
+  for (uint32_t k = lane; k < count; k += kWarp) bufA[k] = (T)unpack_at(vwords, k, vh.bits, vh.minv);
+  __syncwarp();
+  T* cur = bufA;
+  T* nxt = bufB;
+  const int L = R > D ? R : D;
+  for (int i = L - 1; i >= 0; --i) {
+    if (i < D) {
+      // undo delta i: cur holds count deltas, result = count+1 values (or the
+      // layer saw an empty list: cin == 0 and nothing to do)
+      const uint32_t c_in = cin[i];
+      if (c_in == 0 && count != 0) return false;
+      if (c_in != 0) {
+      if (c_in != count + 1 || c_in > cap) return false;
+      uint64_t carry = firsts[i];
+      if (lane == 0) nxt[0] = (T)carry;
+      for (uint32_t base = 0; base < count; base += kWarp) {
+        const uint32_t k = base + lane;
+        uint64_t v = (k < count) ? (uint64_t)cur[k] : 0ull;
+        v = warp_incl_scan_u64(v, lane) + carry;
+        if (k < count) nxt[k + 1] = (T)v;
+        carry = __shfl_sync(kFull, v, 31);
+      }
+      count += 1;
+      __syncwarp();
+      T* t = cur; cur = nxt; nxt = t;
+      }
+    }
+    if (i < R) {
+      // expand with runs_i: cur holds `count` values, runs_i holds `count` lengths
+      const StreamHdr rh = run_hdr[i];
+      if (rh.count != count) return false;
+      const uint64_t* rwords = (const uint64_t*)(payload + run_off[i]);
+      // starts = exclusive scan of run lengths
+      uint32_t carry = 0;
+      for (uint32_t base = 0; base < count; base += kWarp) {
+        const uint32_t k = base + lane;
+        const uint32_t len = (k < count) ? (uint32_t)unpack_at(rwords, k, rh.bits, rh.minv) : 0u;
+        const uint32_t incl = warp_incl_scan_u32(len, lane) + carry;
+        if (k < count) runs[k] = (uint16_t)min(incl - len, 0xffffu);
+        carry = __shfl_sync(kFull, incl, 31);
+        if (carry > cap) return false;
+      }
+      const uint32_t total = carry;
+      if (total > cap || total < count) return false;
+      // head flags -> run index per output element via max-scan
+      for (uint32_t j = lane; j < total; j += kWarp) idx[j] = 0;
+      __syncwarp();
+      for (uint32_t k = lane; k < count; k += kWarp) idx[runs[k]] = (uint16_t)k;
+      __syncwarp();
+      uint32_t mcarry = 0;
+      for (uint32_t base = 0; base < total; base += kWarp) {
+        const uint32_t j = base + lane;
+        uint32_t r = (j < total) ? (uint32_t)idx[j] : 0u;
+        r = max(warp_incl_max_u32(r, lane), mcarry);
+        if (j < total) nxt[j] = cur[r];
+        mcarry = __shfl_sync(kFull, r, 31);
+      }
+      count = total;
+      __syncwarp();
+      T* t = cur; cur = nxt; nxt = t;
+    }
+  }
+  if (count != n_out) return false;
+  // coalesced write-out (out is at least TS-aligned: chunk pointers are 8-aligned
+  // and partitions are multiples of TS)
+  T* o = (T*)out;
+  for (uint32_t k = lane; k < count; k += kWarp) o[k] = cur[k];
+  return true;
+}
+
+struct CascHeader {
+  uint32_t magic, uncompressed, part_bytes, num_parts;
+  int type, R, D, bp;
+};
+
+__device__ __forceinline__ bool casc_read_header(const uint8_t* in, size_t in_bytes, CascHeader& h) {
+  if (in_bytes < 20 || ((uintptr_t)in & 7)) return false;
+  const uint32_t* w = (const uint32_t*)in;
+  h.magic = w[0];
+  const uint32_t cfg = w[1];
+  h.type = cfg & 0xff; h.R = (cfg >> 8) & 0xff; h.D = (cfg >> 16) & 0xff; h.bp = (cfg >> 24) & 0xff;
+  h.uncompressed = w[2]; h.part_bytes = w[3]; h.num_parts = w[4];
+  if (h.magic != kCascMagic) return false;
+  const uint32_t ts = casc_type_size(h.type);
+  if (ts == 0 || h.R > 7 || h.D > 7) return false;
+  if (h.part_bytes == 0 || h.part_bytes > kCascMaxPart || (h.part_bytes % ts)) return false;
+  if ((uint64_t)h.num_parts * h.part_bytes < h.uncompressed) return false;
+  if (h.num_parts && (uint64_t)(h.num_parts - 1) * h.part_bytes >= h.uncompressed) return false;
+  if (h.uncompressed % ts) return false;
+  if (20ull + 4ull * (h.num_parts + 1ull) > in_bytes) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(kCascWarps * 32)
+cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
+                           const size_t* __restrict__ comp_bytes,
+                           const size_t* __restrict__ out_caps,
+                           size_t* actual_bytes, size_t batch,
+                           void* const* __restrict__ out_ptrs,
+                           nvcompStatus_t* statuses,
+                           unsigned long long* ticket) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ unsigned long long s_chunk;
+  __shared__ int s_fail;
+  const int lane = lane_id();
+  const int w = threadIdx.x >> 5;
+  size_t static_next = blockIdx.x;
+  while (true) {
+    if (threadIdx.x == 0) {
+      s_chunk = ticket ? atomicAdd(ticket, 1ull) : (unsigned long long)static_next;
+      s_fail = 0;
+    }
+    static_next += gridDim.x;
+    __syncthreads();
+    const size_t c = (size_t)s_chunk;
+    if (c >= batch) break;
+    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
+    const size_t in_bytes = comp_bytes[c];
+    uint8_t* out = (uint8_t*)out_ptrs[c];
+    const size_t cap = out_caps[c];
+    CascHeader h;
+    bool ok = casc_read_header(in, in_bytes, h);
+    if (ok && (h.uncompressed > cap || ((uintptr_t)out & (casc_type_size(h.type) - 1)))) ok = false;
+    if (ok) {
+      const uint32_t* part_off = (const uint32_t*)(in + 20);
+      const bool fast = h.part_bytes <= kCascFastPart;
+      const int nw = fast ? kCascWarps : 1;
+      uint8_t* sm = fast ? smem + (size_t)w * kCascSmemPerWarp : smem;
+      const uint32_t P = fast ? kCascFastPart : kCascMaxPart;
+      if (w < nw) {
+        for (uint32_t p = w; p < h.num_parts; p += nw) {
+          const uint32_t o0 = part_off[p], o1 = part_off[p + 1];
+          bool pok = (o0 & 7) == 0 && o0 <= o1 && o1 <= in_bytes;
+          if (pok) {
+            const uint32_t begin = p * h.part_bytes;
+            const uint32_t nbytes = min(h.part_bytes, h.uncompressed - begin);
+            const uint32_t ts = casc_type_size(h.type);
+            switch (ts) {
+              case 1: pok = casc_decode_part<1>(in + o0, o1 - o0, out + begin, nbytes, h.R, h.D, sm, P, lane); break;
+              case 2: pok = casc_decode_part<2>(in + o0, o1 - o0, out + begin, nbytes / 2, h.R, h.D, sm, P, lane); break;
+              case 4: pok = casc_decode_part<4>(in + o0, o1 - o0, out + begin, nbytes / 4, h.R, h.D, sm, P, lane); break;
+              default: pok = casc_decode_part<8>(in + o0, o1 - o0, out + begin, nbytes / 8, h.R, h.D, sm, P, lane); break;
+            }
+          }
+          if (!pok && lane == 0) s_fail = 1;
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const bool good = ok && !s_fail;
+      if (actual_bytes) actual_bytes[c] = good ? (size_t)h.uncompressed : 0;
+      if (statuses) statuses[c] = good ? nvcompSuccess : nvcompErrorCannotDecompress;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void cascaded_size_kernel(const void* const* __restrict__ comp_ptrs,
+                                     const size_t* __restrict__ comp_bytes,
+                                     size_t* out_sizes, size_t batch) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= batch) return;
+  CascHeader h;
+  const bool ok = casc_read_header((const uint8_t*)comp_ptrs[c], comp_bytes[c], h);
+  out_sizes[c] = ok ? (size_t)h.uncompressed : 0;
+}
+
+// ---------------------------------------------------------------------------
+// Compression: one warp per chunk walks its partitions in order, so partition
+// payloads are appended without a compaction pass.
+// per-warp smem: A [P] | B [P] | pack words [P + 64] | runs u16 [P elements]
+// ---------------------------------------------------------------------------
+template <int TS>
+__device__ __forceinline__ uint64_t load_elem(const uint8_t* p, uint32_t k) {
+  return (uint64_t)((const typename Elem<TS>::T*)p)[k];
+}
+
+// min/max over count values produced by f(k), signed or unsigned compare on TS bytes
+template <int TS, bool SIGNED, class F>
+__device__ __forceinline__ void warp_minmax(F f, uint32_t count, uint64_t& mn, uint64_t& mx, int lane) {
+  uint64_t lo = ~0ull, hi = 0ull;   // in biased (order-preserving unsigned) space
+  const uint64_t bias = SIGNED ? (1ull << 63) : 0ull;
+  for (uint32_t k = lane; k < count; k += kWarp) {
+    uint64_t v = f(k);
+    v = (SIGNED ? sext<TS>(v) : v) ^ bias;
+    lo = min(lo, v); hi = max(hi, v);
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(kFull, lo, d));
+    hi = max(hi, __shfl_xor_sync(kFull, hi, d));
+  }
+  mn = lo ^ bias; mx = hi ^ bias;
+}
+
+// Pack count values f(k) into dst (global, 8-aligned) via smem word buffer.
+// Returns bytes written.  SIGNED selects the ordering used for the minimum.
+template <int TS, class F>
+__device__ uint32_t casc_pack_stream(F f, uint32_t count, bool use_bp, bool is_signed, uint32_t raw_bits,
+                                     uint8_t* dst, unsigned long long* words, int lane) {
+  uint64_t mn = 0, mx = 0;
+  uint32_t bits = raw_bits;
+  if (use_bp) {
+    if (count == 0) { bits = 0; }
+    else {
+      if (is_signed) warp_minmax<TS, true>(f, count, mn, mx, lane);
+      else warp_minmax<TS, false>(f, count, mn, mx, lane);
+      const uint64_t range = mx - mn;   // wrapping subtract is exact in both orderings
+      bits = range ? 64 - __clzll((long long)range) : 0;
+    }
+  }
+  const uint32_t nwords = (uint32_t)(((uint64_t)count * bits + 63) / 64);
+  for (uint32_t i = lane; i < nwords + 1; i += kWarp) words[i] = 0ull;
+  __syncwarp();
+  if (bits) {
+    const uint64_t mask = bits < 64 ? ((1ull << bits) - 1ull) : ~0ull;
+    for (uint32_t k = lane; k < count; k += kWarp) {
+      uint64_t v = f(k);
+      if (use_bp) v = (is_signed ? sext<TS>(v) : v) - mn;
+      v &= mask;
+      const uint64_t bitpos = (uint64_t)k * bits;
+      const uint32_t w = (uint32_t)(bitpos >> 6), s = (uint32_t)(bitpos & 63);
+      atomicOr(&words[w], v << s);
+      if (s + bits > 64) atomicOr(&words[w + 1], v >> (64 - s));
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    ((uint32_t*)dst)[0] = count;
+    ((uint32_t*)dst)[1] = bits;
+    *(uint64_t*)(dst + 8) = use_bp ? mn : 0ull;
+  }
+  unsigned long long* d64 = (unsigned long long*)(dst + 16);
+  for (uint32_t i = lane; i < nwords; i += kWarp) d64[i] = words[i];
+  __syncwarp();
+  return 16u + 8u * nwords;
+}
+
+template <int TS>
+__device__ uint32_t casc_encode_part(const uint8_t* __restrict__ in, uint32_t n, int R, int D, bool use_bp,
+                                     bool type_signed, uint8_t* dst, uint8_t* sm, uint32_t P, int lane) {
+  using T = typename Elem<TS>::T;
+  T* cur = (T*)sm;
+  T* nxt = (T*)(sm + P);
+  unsigned long long* words = (unsigned long long*)(sm + 2 * P);          // P + 64 bytes
+  uint16_t* runs = (uint16_t*)(sm + 3 * P + 64);                           // 2 * (P/TS) bytes max
+  for (uint32_t k = lane; k < n; k += kWarp) cur[k] = ((const T*)in)[k];
+  __syncwarp();
+  uint32_t count = n;
+  uint32_t off = 8u * (uint32_t)D + ((4u * (uint32_t)D + 7u) & ~7u);
+  uint64_t* firsts = (uint64_t*)dst;
+  uint32_t* cin = (uint32_t*)(dst + 8u * (uint32_t)D);
+  if (lane < 2 * D) cin[lane] = 0;   // also clears the pad word
+  __syncwarp();
+  const int L = R > D ? R : D;
+  bool had_delta = false;
+  for (int i = 0; i < L; ++i) {
+    if (i < R) {
+      // run-length encode cur[0..count) -> nxt values, runs lengths
+      uint32_t carry = 0;
+      for (uint32_t base = 0; base < count; base += kWarp) {
+        const uint32_t k = base + lane;
+        const bool head = (k < count) && (k == 0 || cur[k] != cur[k - 1]);
+        const unsigned m = __ballot_sync(kFull, head);
+        const uint32_t pos = carry + __popc(m & ((1u << lane) - 1u));
+        if (head) { nxt[pos] = cur[k]; runs[pos] = (uint16_t)k; }   // runs[] holds start index for now
+        carry += __popc(m);
+      }
+      const uint32_t m_runs = carry;
+      __syncwarp();
+      // lengths = next start - start
+      auto run_len = [&](uint32_t k) -> uint64_t {
+        const uint32_t s0 = runs[k];
+        const uint32_t s1 = (k + 1 < m_runs) ? (uint32_t)runs[k + 1] : count;
+        return (uint64_t)(s1 - s0);
+      };
+      off += casc_pack_stream<2>(run_len, m_runs, use_bp, false, 16, dst + off, words, lane);
+      count = m_runs;
+      T* t = cur; cur = nxt; nxt = t;
+      __syncwarp();
+    }
+    if (i < D) {
+      if (lane == 0) { firsts[i] = count ? (uint64_t)cur[0] : 0ull; cin[i] = count; }
+      for (uint32_t k = lane; k + 1 < count; k += kWarp) nxt[k] = (T)(cur[k + 1] - cur[k]);
+      count = count ? count - 1 : 0;
+      had_delta = true;
+      T* t = cur; cur = nxt; nxt = t;
+      __syncwarp();
+    }
+  }
+  auto val = [&](uint32_t k) -> uint64_t { return (uint64_t)cur[k]; };
+  // signedness only matters for the min/max of un-delta'd values (doc/cascaded_overview.md:35)
+  off += casc_pack_stream<TS>(val, count, use_bp, had_delta ? true : type_signed, 8 * TS, dst + off, words, lane);
+  return off;
+}
+
+constexpr uint32_t kCascCompSmemPerWarp(uint32_t P) { return 3 * P + 64 + 2 * P + 64; }
+
+__global__ void __launch_bounds__(kCascWarps * 32)
+cascaded_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* __restrict__ in_bytes,
+                         size_t batch, void* const* __restrict__ out_ptrs, size_t* out_bytes,
+                         nvcompBatchedCascadedOpts_t opts, uint32_t smem_per_warp,
+                         unsigned long long* ticket) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = lane_id();
+  const int w = threadIdx.x >> 5;
+  uint8_t* sm = smem + (size_t)w * smem_per_warp;
+  const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + w;
+  const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+  WarpTicket sched(ticket, warp_global, warps_total);
+  const uint32_t ts = casc_type_size(opts.type);
+  const uint32_t P = (uint32_t)opts.chunk_size;
+  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+    const uint8_t* in = (const uint8_t*)in_ptrs[c];
+    const uint32_t n = (uint32_t)in_bytes[c];
+    uint8_t* out = (uint8_t*)out_ptrs[c];
+    const uint32_t num_parts = (n + P - 1) / P;
+    if (lane == 0) {
+      uint32_t* hw = (uint32_t*)out;
+      hw[0] = kCascMagic;
+      hw[1] = (uint32_t)(opts.type & 0xff) | ((uint32_t)opts.num_RLEs << 8) | ((uint32_t)opts.num_deltas << 16)
+              | ((uint32_t)(opts.use_bp ? 1 : 0) << 24);
+      hw[2] = n; hw[3] = P; hw[4] = num_parts;
+    }
+    uint32_t* part_off = (uint32_t*)(out + 20);
+    uint32_t off = (20u + 4u * (num_parts + 1) + 7u) & ~7u;
+    for (uint32_t p = 0; p < num_parts; ++p) {
+      if (lane == 0) part_off[p] = off;
+      const uint32_t begin = p * P;
+      const uint32_t nb = min(P, n - begin);
+      uint32_t sz;
+      switch (ts) {
+        case 1: sz = casc_encode_part<1>(in + begin, nb, opts.num_RLEs, opts.num_deltas, opts.use_bp != 0,
+                                         casc_type_signed(opts.type), out + off, sm, P, lane); break;
+        case 2: sz = casc_encode_part<2>(in + begin, nb / 2, opts.num_RLEs, opts.num_deltas, opts.use_bp != 0,
+                                         casc_type_signed(opts.type), out + off, sm, P, lane); break;
+        case 4: sz = casc_encode_part<4>(in + begin, nb / 4, opts.num_RLEs, opts.num_deltas, opts.use_bp != 0,
+                                         casc_type_signed(opts.type), out + off, sm, P, lane); break;
+        default: sz = casc_encode_part<8>(in + begin, nb / 8, opts.num_RLEs, opts.num_deltas, opts.use_bp != 0,
+                                          casc_type_signed(opts.type), out + off, sm, P, lane); break;
+      }
+      off += (sz + 7u) & ~7u;
+    }
+    if (lane == 0) { part_off[num_parts] = off; out_bytes[c] = off; }
+    __syncwarp();
+  }
+}
+
+inline nvcompStatus_t casc_check_opts(const nvcompBatchedCascadedOpts_t& o) {
+  const uint32_t ts = casc_type_size(o.type);
+  if (ts == 0) return nvcompErrorInvalidValue;
+  if (o.num_RLEs < 0 || o.num_RLEs > 7 || o.num_deltas < 0 || o.num_deltas > 7) return nvcompErrorInvalidValue;
+  if (o.chunk_size < 512 || o.chunk_size > kCascMaxPart || (o.chunk_size % 8)) return nvcompErrorInvalidValue;
+  return nvcompSuccess;
+}
+
+// worst-case bytes of one partition payload
+inline size_t casc_part_bound(const nvcompBatchedCascadedOpts_t& o) {
+  const size_t ts = casc_type_size(o.type);
+  const size_t n = o.chunk_size / ts;
+  size_t b = 8 * (size_t)o.num_deltas + ((4 * (size_t)o.num_deltas + 7) & ~(size_t)7);
+  b += (size_t)o.num_RLEs * (16 + ((n * 16 + 63) / 64) * 8);   // run streams: <= 16 bits each
+  b += 16 + ((n * ts * 8 + 63) / 64) * 8;                       // value stream
+  return (b + 7) & ~(size_t)7;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+nvcompStatus_t nvcompBatchedCascadedCompressGetTempSize(
+    size_t, size_t max_chunk, nvcompBatchedCascadedOpts_t opts, size_t* temp_bytes) {
+  if (!temp_bytes) return nvcompErrorInvalidValue;
+  const nvcompStatus_t st = casc_check_opts(opts);
+  if (st != nvcompSuccess) return st;
+  if (max_chunk > nvcompCascadedCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
+  *temp_bytes = kSchedBytes;
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedCascadedCompressGetTempSizeEx(
+    size_t b, size_t m, nvcompBatchedCascadedOpts_t o, size_t* t, const size_t) {
+  return nvcompBatchedCascadedCompressGetTempSize(b, m, o, t);
+}
+
+nvcompStatus_t nvcompBatchedCascadedCompressGetMaxOutputChunkSize(
+    size_t max_chunk, nvcompBatchedCascadedOpts_t opts, size_t* max_compressed_bytes) {
+  if (!max_compressed_bytes) return nvcompErrorInvalidValue;
+  const nvcompStatus_t st = casc_check_opts(opts);
+  if (st != nvcompSuccess) return st;
+  if (max_chunk > nvcompCascadedCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
+  const size_t parts = (max_chunk + opts.chunk_size - 1) / opts.chunk_size;
+  *max_compressed_bytes = ((20 + 4 * (parts + 1) + 7) & ~(size_t)7) + parts * casc_part_bound(opts) + 8;
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedCascadedCompressAsync(
+    const void* const* in_ptrs, const size_t* in_bytes, size_t max_chunk, size_t batch,
+    void* temp, size_t temp_bytes, void* const* out_ptrs, size_t* out_bytes,
+    nvcompBatchedCascadedOpts_t opts, cudaStream_t stream) {
+  const nvcompStatus_t st = casc_check_opts(opts);
+  if (st != nvcompSuccess) return st;
+  if (max_chunk > nvcompCascadedCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
+  if (batch == 0) return nvcompSuccess;
+  if (!in_ptrs || !in_bytes || !out_ptrs || !out_bytes) return nvcompErrorInvalidValue;
+  unsigned long long* ticket = nullptr;
+  if (temp && temp_bytes >= kSchedBytes) {
+    ticket = (unsigned long long*)temp;
+    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+  }
+  const uint32_t per_warp = (kCascCompSmemPerWarp((uint32_t)opts.chunk_size) + 15u) & ~15u;
+  int nw = (int)((220u * 1024u) / per_warp);
+  if (nw > kCascWarps) nw = kCascWarps;
+  if (nw < 1) return nvcompErrorInvalidValue;
+  const size_t smem = (size_t)nw * per_warp;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(cascaded_compress_kernel,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+  const int grid = persistent_grid(ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm), batch, nw);
+  cascaded_compress_kernel<<<grid, nw * 32, smem, stream>>>(
+      in_ptrs, in_bytes, batch, out_ptrs, out_bytes, opts, per_warp, ticket);
+  B200_CUDA_TRY(cudaGetLastError());
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedCascadedDecompressGetTempSize(size_t, size_t, size_t* temp_bytes) {
+  if (!temp_bytes) return nvcompErrorInvalidValue;
+  *temp_bytes = kSchedBytes;
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedCascadedDecompressGetTempSizeEx(size_t n, size_t m, size_t* t, size_t) {
+  return nvcompBatchedCascadedDecompressGetTempSize(n, m, t);
+}
+
+nvcompStatus_t nvcompBatchedCascadedGetDecompressSizeAsync(
+    const void* const* comp_ptrs, const size_t* comp_bytes, size_t* out_sizes,
+    size_t batch, cudaStream_t stream) {
+  if (batch == 0) return nvcompSuccess;
+  if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
+  cascaded_size_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(comp_ptrs, comp_bytes, out_sizes, batch);
+  B200_CUDA_TRY(cudaGetLastError());
+  return nvcompSuccess;
+}
+
+nvcompStatus_t nvcompBatchedCascadedDecompressAsync(
+    const void* const* comp_ptrs, const size_t* comp_bytes, const size_t* out_caps,
+    size_t* actual_bytes, size_t batch, void* const temp, size_t temp_bytes,
+    void* const* out_ptrs, nvcompStatus_t* statuses, cudaStream_t stream) {
+  if (batch == 0) return nvcompSuccess;
+  if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
+  unsigned long long* ticket = nullptr;
+  if (temp && temp_bytes >= kSchedBytes) {
+    ticket = (unsigned long long*)temp;
+    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(cascaded_decompress_kernel,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCascSmem));
+    attr_set = true;
+  }
+  const int grid = persistent_grid(2, batch, 1);
+  cascaded_decompress_kernel<<<grid, kCascWarps * 32, kCascSmem, stream>>>(
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+  B200_CUDA_TRY(cudaGetLastError());
+  return nvcompSuccess;
+}
+
+}  // extern "C"

@@ -62,8 +62,6 @@ __device__ __forceinline__ void lz77_compress_chunk(
       h = hash4(v);
       cand = table[h];
     }
-    __syncwarp();
-    if (valid) table[h] = (uint16_t)p;
     bool is_match = false;
     uint32_t cpos = 0;
     if (valid) {
@@ -72,14 +70,34 @@ __device__ __forceinline__ void lz77_compress_chunk(
       if (cpos >= p) cpos = (cpos >= 0x10000u) ? cpos - 0x10000u : p;  // -> invalid when cpos == p
       if (cpos < p && (p - cpos) <= 65535u) is_match = (load_u32(in + cpos) == v);
     }
+    // Intra-group candidates: the hash table cannot yet contain positions of this same
+    // round, so short-period repeats (typed run-length data: period 1/2/4/8 elements)
+    // are caught by comparing against the lanes d positions below.
+    {
+      const uint32_t stride = step * accel;
+#pragma unroll
+      for (int d = 1; d <= 8; d <<= 1) {
+        const uint32_t vo = __shfl_up_sync(kFull, v, d);
+        const bool vvalid = __shfl_up_sync(kFull, valid ? 1 : 0, d) != 0;
+        if (!is_match && valid && vvalid && lane >= d && vo == v && (uint32_t)d * stride <= 65535u) {
+          is_match = true;
+          cpos = p - (uint32_t)d * stride;
+        }
+      }
+    }
     const unsigned m = __ballot_sync(kFull, is_match);
+    // Insert only the positions this round consumes (up to and including the match
+    // position): later positions are probed again next round and must still find
+    // their older candidate, not themselves.
+    const int first = m ? __ffs(m) - 1 : 31;
+    if (valid && lane <= first) table[h] = (uint16_t)p;
+    __syncwarp();
     if (m == 0) {
       pos += 32u * step * accel;
       if (misses < 64) ++misses;
       continue;
     }
     misses = 0;
-    const int first = __ffs(m) - 1;
     const uint32_t mp = __shfl_sync(kFull, p, first);
     const uint32_t mc = __shfl_sync(kFull, cpos, first);
     // cooperative forward extension

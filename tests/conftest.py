@@ -39,6 +39,26 @@ class Oracle:
             fn = getattr(self.lib, f"oracle_{name}_bound")
             fn.argtypes, fn.restype = [sz], sz
 
+        self.lib.oracle_cascaded_compress.argtypes = [u8p, sz, u8p, sz, sz, C.c_uint, C.c_int, C.c_int, C.c_int]
+        self.lib.oracle_cascaded_compress.restype = C.c_long
+        self.lib.oracle_bitcomp_compress.argtypes = [u8p, sz, u8p, sz, C.c_uint, C.c_uint]
+        self.lib.oracle_bitcomp_compress.restype = C.c_long
+        self.lib.oracle_ans_compress.argtypes = [u8p, sz, u8p, sz]
+        self.lib.oracle_ans_compress.restype = C.c_long
+
+    def compress_typed(self, codec: str, data: bytes, **kw) -> bytes:
+        cap = 24 * len(data) + 65536
+        out = C.create_string_buffer(cap)
+        if codec == "cascaded":
+            r = self.lib.oracle_cascaded_compress(data, len(data), out, cap, kw.get("chunk_size", 4096), kw["type"],
+                                                  kw["num_RLEs"], kw["num_deltas"], kw["use_bp"])
+        elif codec == "bitcomp":
+            r = self.lib.oracle_bitcomp_compress(data, len(data), out, cap, kw["algo"], kw["type"])
+        else:
+            r = self.lib.oracle_ans_compress(data, len(data), out, cap)
+        assert r >= 0, (codec, kw)
+        return out.raw[:r]
+
     def decompress(self, codec: str, data: bytes, cap: int):
         out = C.create_string_buffer(max(cap, 1))
         r = getattr(self.lib, f"oracle_{codec}_decompress")(data, len(data), out, cap)
