@@ -330,7 +330,7 @@ __global__ void cascaded_size_kernel(const void* const* __restrict__ comp_ptrs,
 // ---------------------------------------------------------------------------
 // Compression: one warp per chunk walks its partitions in order, so partition
 // payloads are appended without a compaction pass.
-// per-warp smem: A [P] | B [P] | pack words [P + 64] | runs u16 [P elements]
+// per-warp smem: A [P] | B [P] | pack words [2P + 64] | runs u16 [P elements]
 // ---------------------------------------------------------------------------
 template <int TS>
 __device__ __forceinline__ uint64_t load_elem(const uint8_t* p, uint32_t k) {
@@ -404,8 +404,9 @@ __device__ uint32_t casc_encode_part(const uint8_t* __restrict__ in, uint32_t n,
   using T = typename Elem<TS>::T;
   T* cur = (T*)sm;
   T* nxt = (T*)(sm + P);
-  unsigned long long* words = (unsigned long long*)(sm + 2 * P);          // P + 64 bytes
-  uint16_t* runs = (uint16_t*)(sm + 3 * P + 64);                           // 2 * (P/TS) bytes max
+  // pack buffer: a run-length stream of 1-byte elements can need 16 bits per run -> 2*P bytes
+  unsigned long long* words = (unsigned long long*)(sm + 2 * P);          // 2*P + 64 bytes
+  uint16_t* runs = (uint16_t*)(sm + 4 * P + 64);                           // 2 * (P/TS) bytes max
   for (uint32_t k = lane; k < n; k += kWarp) cur[k] = ((const T*)in)[k];
   __syncwarp();
   uint32_t count = n;
@@ -456,7 +457,7 @@ __device__ uint32_t casc_encode_part(const uint8_t* __restrict__ in, uint32_t n,
   return off;
 }
 
-constexpr uint32_t kCascCompSmemPerWarp(uint32_t P) { return 3 * P + 64 + 2 * P + 64; }
+constexpr uint32_t kCascCompSmemPerWarp(uint32_t P) { return 4 * P + 64 + 2 * P + 64; }
 
 __global__ void __launch_bounds__(kCascWarps * 32)
 cascaded_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* __restrict__ in_bytes,

@@ -125,13 +125,32 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
   const uint4* s16 = (const uint4*)(src - mis);
   uint4* d16 = (uint4*)dst;
   if (mis == 0) {
-    for (uint32_t v = lane; v < nvec; v += kWarp) {
+    // 4 vectors in flight per lane: all loads of a round are issued before the stores
+    uint32_t v = lane;
+    for (; v + 3 * kWarp < nvec; v += 4 * kWarp) {
+      uint4 a0 = RO ? ld_nc_v4(s16 + v) : ld_v4(s16 + v);
+      uint4 a1 = RO ? ld_nc_v4(s16 + v + kWarp) : ld_v4(s16 + v + kWarp);
+      uint4 a2 = RO ? ld_nc_v4(s16 + v + 2 * kWarp) : ld_v4(s16 + v + 2 * kWarp);
+      uint4 a3 = RO ? ld_nc_v4(s16 + v + 3 * kWarp) : ld_v4(s16 + v + 3 * kWarp);
+      st_v4(d16 + v, a0); st_v4(d16 + v + kWarp, a1);
+      st_v4(d16 + v + 2 * kWarp, a2); st_v4(d16 + v + 3 * kWarp, a3);
+    }
+    for (; v < nvec; v += kWarp) {
       uint4 a = RO ? ld_nc_v4(s16 + v) : ld_v4(s16 + v);
       st_v4(d16 + v, a);
     }
   } else {
     const uint32_t ws = mis >> 2, bs = (mis & 3) * 8;
-    for (uint32_t v = lane; v < nvec; v += kWarp) {
+    uint32_t v = lane;
+    for (; v + kWarp < nvec; v += 2 * kWarp) {
+      uint4 a0 = RO ? ld_nc_v4(s16 + v) : ld_v4(s16 + v);
+      uint4 b0 = RO ? ld_nc_v4(s16 + v + 1) : ld_v4(s16 + v + 1);
+      uint4 a1 = RO ? ld_nc_v4(s16 + v + kWarp) : ld_v4(s16 + v + kWarp);
+      uint4 b1 = RO ? ld_nc_v4(s16 + v + kWarp + 1) : ld_v4(s16 + v + kWarp + 1);
+      st_v4(d16 + v, realign16(a0, b0, ws, bs));
+      st_v4(d16 + v + kWarp, realign16(a1, b1, ws, bs));
+    }
+    for (; v < nvec; v += kWarp) {
       uint4 a = RO ? ld_nc_v4(s16 + v) : ld_v4(s16 + v);
       uint4 b = RO ? ld_nc_v4(s16 + v + 1) : ld_v4(s16 + v + 1);
       st_v4(d16 + v, realign16(a, b, ws, bs));

@@ -1,0 +1,371 @@
+// lz_decode.cuh -- lane-parallel LZ77 (LZ4 / Snappy) chunk decoder for B200.
+//
+// One warp owns one chunk.  The decoder is organised around the observation that on
+// tabular data a 64 KB chunk holds 10-15 thousand *short* tokens (4-8 output bytes
+// each), so throughput is bounded by warp-instructions per token, not by bytes:
+//
+//  * FAST PATH (short tokens).  The 32 lanes look at 32 consecutive input bytes.
+//    Every lane parses the byte under it as if it were a token start (speculative
+//    parse), the true token chain is recovered with 4 rounds of pointer doubling
+//    (__reduce_or_sync + __shfl_sync), a warp scan of the token output lengths gives
+//    every token its output position, literals are scattered in one pass straight from
+//    registers, and the matches are copied one token per lane in dependency rounds
+//    (a match is ready once everything below its source end has been written).
+//    ~10 tokens retire per iteration instead of one.
+//  * The most recent 4 KB of output live in a per-warp shared-memory ring, so match
+//    sources are read at shared-memory latency; completed 512-byte blocks are flushed
+//    to HBM with 16-byte aligned vector stores (full-line writes).  Matches that reach
+//    further back than the ring read the already flushed bytes from global memory.
+//  * SLOW PATH (long tokens: length-extension bytes, >18-byte matches, ...).  The ring
+//    is flushed and the token is executed by the whole warp directly on global memory
+//    with 16-byte vector copies (common.cuh warp_copy / warp_match_copy), then the ring
+//    restarts empty.  Runs of long tokens stay in this mode.
+//
+// Format specifics (token grammar, stream end, size limits) come from a Parse policy.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr uint32_t kRingBytes = 4096;
+constexpr uint32_t kRingMask = kRingBytes - 1;
+constexpr uint32_t kFlushBlock = 512;
+// A match source is served from the ring only if it is younger than this many bytes
+// (ring size minus the largest output one fast iteration can append, minus alignment slack).
+constexpr uint32_t kRingReach = kRingBytes - 1024 - 16;
+
+struct LzState {
+  const uint8_t* in;
+  uint32_t in_n;
+  uint8_t* out;        // chunk output base (any alignment)
+  uint64_t out_cap;    // capacity (LZ4) or exact size (Snappy)
+  uint32_t ip;         // input cursor
+  uint32_t op;         // output cursor (bytes produced)
+  uint32_t flushed;    // output bytes already in global memory
+  uint32_t ring_lo;    // lowest output offset whose bytes are valid in the ring
+  uint32_t align;      // (uintptr_t)out & 15: ring index = (offset + align) & mask
+  uint8_t* ring;       // shared memory, kRingBytes
+};
+
+__device__ __forceinline__ uint32_t ring_idx(const LzState& s, uint32_t off) {
+  return (off + s.align) & kRingMask;
+}
+
+// Write ring bytes [s.flushed, upto) to global memory.  Vector stores where the global
+// address is 16-byte aligned, byte stores for ragged ends.
+__device__ __forceinline__ void lz_flush(LzState& s, uint32_t upto, int lane) {
+  uint32_t f = s.flushed;
+  if (upto <= f) return;
+  __syncwarp();
+  // ragged head up to the next 16-byte boundary (in aligned space)
+  uint32_t head = (16u - ((f + s.align) & 15u)) & 15u;
+  if (head > upto - f) head = upto - f;
+  if ((uint32_t)lane < head) s.out[f + lane] = s.ring[ring_idx(s, f + lane)];
+  f += head;
+  const uint32_t nvec = (upto - f) >> 4;
+  for (uint32_t v = lane; v < nvec; v += kWarp) {
+    const uint32_t o = f + (v << 4);
+    const uint4 d = *(const uint4*)(s.ring + ring_idx(s, o));
+    st_v4((uint4*)(s.out + o), d);
+  }
+  f += nvec << 4;
+  const uint32_t tail = upto - f;
+  if ((uint32_t)lane < tail) s.out[f + lane] = s.ring[ring_idx(s, f + lane)];
+  s.flushed = upto;
+}
+
+// Flush every completed 512-byte block (keeps global stores full-line).
+__device__ __forceinline__ void lz_flush_blocks(LzState& s, int lane) {
+  const uint32_t lim = ((s.op + s.align) & ~(kFlushBlock - 1));
+  if (lim > s.flushed + s.align) lz_flush(s, lim - s.align, lane);
+}
+
+// ---------------------------------------------------------------------------
+// Parse policies.  parse(b0, p, lane) classifies the byte at window position `lane`
+// as a token start: literal length L, match length M, bytes to the next token, where
+// the 2-byte offset sits (rel. to the token) and whether the token needs the slow path.
+// ---------------------------------------------------------------------------
+struct Tok {
+  uint32_t L, M, size, off_at;   // off_at: offset field position relative to token start (0 = none)
+  bool stop;
+  uint32_t kind;                 // format-private
+};
+
+struct Lz4Policy {
+  static constexpr uint32_t kLook = 80;        // fast path needs ip + kLook <= in_n
+  static constexpr uint32_t kMaxFastM = 18;
+  __device__ static __forceinline__ Tok parse(uint32_t b0) {
+    Tok t;
+    t.L = b0 >> 4;
+    const uint32_t mn = b0 & 15u;
+    t.M = mn + 4;
+    t.stop = (t.L == 15u) | (mn == 15u);
+    t.size = 3 + t.L;
+    t.off_at = 1 + t.L;
+    t.kind = 0;
+    return t;
+  }
+  __device__ static __forceinline__ uint32_t offset(const uint8_t* __restrict__ p, const Tok& t) {
+    return load_u16(p + t.off_at);
+  }
+  // does the token starting with byte b0 need the medium / long path?
+  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return (b0 >> 4) == 15u || (b0 & 15u) == 15u; }
+};
+
+struct SnappyPolicy {
+  static constexpr uint32_t kLook = 96;
+  static constexpr uint32_t kMaxFastM = 18;
+  __device__ static __forceinline__ Tok parse(uint32_t b0) {
+    Tok t;
+    const uint32_t kind = b0 & 3u, hi = b0 >> 2;
+    t.kind = kind;
+    t.L = 0; t.M = 0; t.off_at = 1; t.stop = false;
+    if (kind == 0) {
+      t.L = hi + 1; t.size = 1 + t.L; t.off_at = 0;
+      t.stop = t.L > 28u;
+    } else if (kind == 1) {
+      t.M = 4 + (hi & 7u); t.size = 2;
+    } else if (kind == 2) {
+      t.M = hi + 1; t.size = 3;
+      t.stop = t.M > kMaxFastM;
+    } else {
+      t.size = 5; t.stop = true;
+    }
+    return t;
+  }
+  __device__ static __forceinline__ uint32_t offset(const uint8_t* __restrict__ p, const Tok& t) {
+    if (t.kind == 1) return ((uint32_t)(p[0] >> 5) << 8) | p[1];
+    return load_u16(p + 1);
+  }
+  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return parse(b0).stop; }
+};
+
+// Copy one short match (one lane = one token) inside the ring / from global memory.
+__device__ __forceinline__ void lane_match_copy(const LzState& s, uint32_t ring_from, uint32_t dst,
+                                                uint32_t off, uint32_t M) {
+  const uint32_t src = dst - off;
+  uint32_t r = 0;                            // source index modulo off (overlapping matches replicate)
+  for (uint32_t i = 0; i < M; ++i) {
+    const uint32_t sp = src + r;
+    const uint8_t b = (sp >= ring_from) ? s.ring[ring_idx(s, sp)] : s.out[sp];
+    s.ring[ring_idx(s, dst + i)] = b;
+    ++r;
+    if (r == off) r = 0;
+  }
+}
+
+// One fast-path iteration.  Returns number of tokens retired (0: the token at s.ip needs
+// the slow path), or -1 on a malformed stream.
+template <class P>
+__device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
+  const uint8_t* __restrict__ win = s.in + s.ip;
+  const uint32_t b0 = win[lane];
+  const Tok t = P::parse(b0);
+  // --- token chain by pointer doubling -------------------------------------------------
+  const unsigned stopmask = __ballot_sync(kFull, t.stop);
+  const uint32_t nxt0 = t.stop ? 64u : (uint32_t)lane + t.size;    // >= 32: leaves the window
+  uint32_t nxt = nxt0;
+  unsigned reach = 1u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool mine = (reach >> lane) & 1u;
+    const unsigned contrib = (mine && nxt < 32u) ? (1u << nxt) : 0u;
+    reach |= __reduce_or_sync(kFull, contrib);
+    const uint32_t hop = __shfl_sync(kFull, nxt, nxt & 31u);
+    nxt = (nxt < 32u) ? hop : nxt;
+  }
+  const unsigned tokmask = reach & ~stopmask;
+  if (tokmask == 0) return 0;
+  const unsigned hitstop = reach & stopmask;
+  const int last = 31 - __clz(tokmask);
+  const uint32_t adv = hitstop ? (uint32_t)(__ffs(hitstop) - 1) : __shfl_sync(kFull, nxt0, last);
+  const bool is_tok = (tokmask >> lane) & 1u;
+
+  // --- per-token fields, output positions ------------------------------------------------
+  uint32_t off = 0;
+  if (is_tok && t.M) off = P::offset(win + lane, t);
+  const uint32_t len = is_tok ? (t.L + t.M) : 0u;
+  uint32_t incl = len;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += o;
+  }
+  const uint32_t total = __shfl_sync(kFull, incl, 31);
+  if ((uint64_t)s.op + total > s.out_cap) return 0;        // let the slow path find the exact error
+  const uint32_t o_lit = s.op + incl - len;
+  const uint32_t o_mat = o_lit + t.L;
+  const bool bad = is_tok && t.M && (off == 0u || off > o_mat);
+  if (__any_sync(kFull, bad)) return -1;
+
+  // --- literals: every window byte finds its token and scatters itself --------------------
+  {
+    const unsigned below = reach & (0xffffffffu >> (31 - lane));   // reach bits <= lane (bit 0 always set)
+    const int tk = 31 - __clz(below);
+    const uint32_t tL = __shfl_sync(kFull, t.L, tk);
+    const uint32_t tO = __shfl_sync(kFull, o_lit, tk);
+    const bool tok_ok = (tokmask >> tk) & 1u;
+    const uint32_t k = (uint32_t)lane - (uint32_t)tk - 1u;          // literal index within token tk
+    if (tok_ok && lane > tk && k < tL) s.ring[ring_idx(s, tO + k)] = (uint8_t)b0;
+    // literal bytes past the window can only belong to the last token
+    const uint32_t lL = __shfl_sync(kFull, t.L, last);
+    const uint32_t lO = __shfl_sync(kFull, o_lit, last);
+    if ((uint32_t)last + 1u + lL > 32u) {
+      const uint32_t k2 = 32u + (uint32_t)lane - (uint32_t)last - 1u;
+      if (k2 < lL) s.ring[ring_idx(s, lO + k2)] = win[32 + lane];
+    }
+  }
+  // --- matches -------------------------------------------------------------------------------
+  // Round 1 copies, one match per lane, every match whose source bytes are already final
+  // (they end at or below the output position of the first match of the window): on tabular
+  // data that is the majority.  The common case (no overlap, source entirely in the ring or
+  // entirely in flushed global memory, no ring wrap-around) is a branch-free unrolled copy in
+  // tiers of 4 bytes with immediate offsets.  The remaining matches depend on output of this
+  // same window and are retired in order, the whole warp copying one match (<= 18 bytes, one
+  // byte per lane) per step.
+  const uint32_t ring_from = max(s.ring_lo, s.op > kRingReach ? s.op - kRingReach : 0u);
+  const bool has_match = is_tok && t.M != 0u;
+  unsigned pending = __ballot_sync(kFull, has_match);
+  const uint32_t src0 = o_mat - off;
+  const uint32_t pack = off | (t.M << 16);
+  if (pending) {
+    const uint32_t src_end = src0 + min(t.M, off);           // exclusive end of the bytes this match reads
+    const uint32_t didx = ring_idx(s, o_mat), sidx = ring_idx(s, src0);
+    const bool in_ring = src0 >= ring_from && sidx <= kRingBytes - 20u;
+    const bool far = src0 + t.M <= ring_from;                // flushed long ago: read from global
+    const bool simple = has_match && off >= t.M && didx <= kRingBytes - 20u && (in_ring || far);
+    uint8_t* const dp = s.ring + didx;
+    const uint8_t* const sp = far ? (const uint8_t*)(s.out + src0) : (const uint8_t*)(s.ring + sidx);
+    __syncwarp();
+    const int first0 = __ffs(pending) - 1;
+    const uint32_t w = __shfl_sync(kFull, o_mat, first0);    // everything below w is final
+    const bool ready = has_match && (src_end <= w);
+    const bool fast = ready && simple;
+    if (fast) {
+      const uint8_t b0 = sp[0], b1 = sp[1], b2 = sp[2], b3 = sp[3];
+      dp[0] = b0;
+      if (t.M > 1) dp[1] = b1;
+      if (t.M > 2) dp[2] = b2;
+      if (t.M > 3) dp[3] = b3;
+    }
+    if (__any_sync(kFull, fast && t.M > 4u)) {
+      if (fast && t.M > 4u) {
+        const uint8_t b0 = sp[4], b1 = sp[5], b2 = sp[6], b3 = sp[7];
+        dp[4] = b0;
+        if (t.M > 5) dp[5] = b1;
+        if (t.M > 6) dp[6] = b2;
+        if (t.M > 7) dp[7] = b3;
+      }
+      if (__any_sync(kFull, fast && t.M > 8u)) {
+        if (fast && t.M > 8u) {
+#pragma unroll
+          for (uint32_t i = 8; i < 18; ++i)
+            if (i < t.M) dp[i] = sp[i];
+        }
+      }
+    }
+    pending &= ~__ballot_sync(kFull, fast);
+    // in-order retirement of everything else
+    while (pending) {
+      __syncwarp();
+      const int f = __ffs(pending) - 1;
+      const uint32_t f_omat = __shfl_sync(kFull, o_mat, f);
+      const uint32_t f_pack = __shfl_sync(kFull, pack, f);
+      const uint32_t f_off = f_pack & 0xffffu, f_M = f_pack >> 16;
+      if ((uint32_t)lane < f_M) {
+        uint32_t r = lane;
+        if (r >= f_off) r %= f_off;                          // overlapping match replicates its period
+        const uint32_t q = f_omat - f_off + r;
+        const uint8_t b = (q >= ring_from) ? s.ring[ring_idx(s, q)] : s.out[q];
+        s.ring[ring_idx(s, f_omat + lane)] = b;
+      }
+      pending &= pending - 1;
+    }
+  }
+  s.op += total;
+  s.ip += adv;
+  return __popc(tokmask);
+}
+
+
+// ---------------------------------------------------------------------------
+// Medium tokens (too long for the lane-parallel path, L + M <= kMediumMax): executed by the
+// whole warp one token at a time but still inside the ring, so the data stays at shared-memory
+// latency and later short matches keep hitting the ring.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kMediumMax = 192;
+
+__device__ __forceinline__ void ring_put_literals(LzState& s, uint32_t dst, const uint8_t* __restrict__ src,
+                                                  uint32_t n, int lane) {
+  for (uint32_t i = lane; i < n; i += kWarp) s.ring[ring_idx(s, dst + i)] = src[i];
+}
+
+// dst[0..n) = dst[-off..] with LZ77 semantics, all inside the ring (far sources from global).
+__device__ __forceinline__ void ring_match(LzState& s, uint32_t dst, uint32_t off, uint32_t n,
+                                           uint32_t ring_from, int lane) {
+  const uint32_t src = dst - off;
+  if (off >= 32u) {
+    // bytes of round k only depend on bytes written in rounds < k
+    for (uint32_t base = 0; base < n; base += kWarp) {
+      const uint32_t j = base + lane;
+      if (j < n) {
+        const uint32_t sp = src + j;
+        const uint8_t b = (sp >= ring_from) ? s.ring[ring_idx(s, sp)] : s.out[sp];
+        s.ring[ring_idx(s, dst + j)] = b;
+      }
+      __syncwarp();
+    }
+  } else {
+    // short period: every byte is src[j mod off], all final before the copy starts
+    uint32_t r = (uint32_t)lane % off;
+    const uint32_t step = 32u % off;
+    for (uint32_t j = lane; j < n; j += kWarp) {
+      const uint32_t sp = src + r;
+      const uint8_t b = (sp >= ring_from) ? s.ring[ring_idx(s, sp)] : s.out[sp];
+      s.ring[ring_idx(s, dst + j)] = b;
+      r += step;
+      if (r >= off) r -= off;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t ring_from_of(const LzState& s) {
+  return max(s.ring_lo, s.op > kRingReach ? s.op - kRingReach : 0u);
+}
+
+// Decode driver shared by LZ4 and Snappy.  P::slow_token(s, lane) executes exactly one token
+// at s.ip directly on global memory (ring already flushed) and returns 1 (continue),
+// 2 (stream finished) or -1 (malformed).
+template <class P>
+__device__ __forceinline__ bool lz_decode_stream(LzState& s, int lane) {
+  while (true) {
+    if (P::at_end(s)) break;
+    // a token that needs the medium / long path is recognised from its first byte: do not pay for
+    // a speculative window parse that would retire nothing
+    if (s.ip + P::kLook <= s.in_n && !P::is_stop(s.in[s.ip])) {
+      const int r = lz_fast_iter<P>(s, lane);
+      if (r < 0) return false;
+      if (r > 0) { lz_flush_blocks(s, lane); continue; }
+    }
+    {
+      // P::medium_token: 1 = token executed inside the ring, 2 = stream finished,
+      // 0 = token too long (falls through to the global-memory path), -1 = malformed
+      const int m = P::medium_token(s, lane);
+      if (m < 0) return false;
+      if (m == 1) { lz_flush_blocks(s, lane); continue; }
+      if (m == 2) break;
+    }
+    lz_flush(s, s.op, lane);
+    __syncwarp();
+    const int r = P::slow_token(s, lane);
+    if (r < 0) return false;
+    s.flushed = s.op;
+    s.ring_lo = s.op;
+    if (r == 2) break;
+  }
+  lz_flush(s, s.op, lane);
+  return true;
+}
+
+}  // namespace b200

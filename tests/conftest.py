@@ -47,7 +47,7 @@ class Oracle:
         self.lib.oracle_ans_compress.restype = C.c_long
 
     def compress_typed(self, codec: str, data: bytes, **kw) -> bytes:
-        cap = 24 * len(data) + 65536
+        cap = 24 * len(data) + 262144
         out = C.create_string_buffer(cap)
         if codec == "cascaded":
             r = self.lib.oracle_cascaded_compress(data, len(data), out, cap, kw.get("chunk_size", 4096), kw["type"],
