@@ -12,7 +12,9 @@ HDRS      := $(wildcard $(SRC_DIR)/*.cuh) $(wildcard $(SRC_DIR)/*.h) $(wildcard 
 ORACLE_SRCS := $(wildcard oracle/*.c)
 ORACLE_LIB  := oracle/liboracle.so
 
-all: $(LIB) $(ORACLE_LIB)
+TESTS_BIN := build/tests/hlif_test
+
+all: $(LIB) $(ORACLE_LIB) $(TESTS_BIN)
 
 $(BUILD_DIR)/%.o: $(SRC_DIR)/%.cu $(HDRS)
 	@mkdir -p $(BUILD_DIR)
@@ -24,6 +26,10 @@ $(LIB): $(OBJS)
 
 $(ORACLE_LIB): $(ORACLE_SRCS) $(wildcard oracle/*.h)
 	gcc -O3 -march=x86-64-v2 -fPIC -shared -Wall -o $@ $(ORACLE_SRCS)
+
+build/tests/hlif_test: tests/cpp/hlif_test.cu $(LIB) $(HDRS)
+	@mkdir -p build/tests
+	$(NVCC) $(ARCH) -std=c++17 -O2 -Iinclude $< -o $@ -Lnvcomp_b200/lib -lnvcomp -Xlinker -rpath=$(CURDIR)/nvcomp_b200/lib
 
 clean:
 	rm -rf $(BUILD_DIR) $(LIB) $(ORACLE_LIB)

@@ -365,7 +365,9 @@ nvcompStatus_t nvcompBatchedANSCompressGetMaxOutputChunkSize(
   const size_t nseg = (max_chunk + kAnsSeg - 1) / kAnsSeg;
   // the encoder falls back to stored mode (16 + n) whenever rANS would be larger, but the
   // rANS attempt is laid out in the output's header area first
-  *max_compressed_bytes = 16 + 512 + 4 * (nseg + 1) + max_chunk + 16;
+  // multiple of 8: callers lay output chunks out at i * max_compressed_bytes (reference
+  // benchmarks/benchmark_template_chunked.cuh:217-232) and ANS streams must be 8-byte aligned
+  *max_compressed_bytes = (16 + 512 + 4 * (nseg + 1) + max_chunk + 16 + 7) & ~(size_t)7;
   return nvcompSuccess;
 }
 

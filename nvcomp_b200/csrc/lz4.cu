@@ -185,7 +185,7 @@ __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t 
   s.in = in; s.in_n = in_n; s.out = out; s.out_cap = out_cap > 0xffffffffull ? 0xffffffffull : out_cap;
   s.ip = 0; s.op = 0; s.flushed = 0; s.ring_lo = 0;
   s.align = (uint32_t)((uintptr_t)out & 15u);
-  s.ring = ring;
+  s.ring = (uint32_t)__cvta_generic_to_shared(ring);
   if (!lz_decode_stream<Lz4Decode>(s, lane)) return false;
   *produced = s.op;
   return true;

@@ -45,11 +45,36 @@ struct LzState {
   uint32_t flushed;    // output bytes already in global memory
   uint32_t ring_lo;    // lowest output offset whose bytes are valid in the ring
   uint32_t align;      // (uintptr_t)out & 15: ring index = (offset + align) & mask
-  uint8_t* ring;       // shared memory, kRingBytes
+  uint32_t ring;       // shared-window address of the kRingBytes ring (32-bit: LDS/STS with immediates)
 };
 
 __device__ __forceinline__ uint32_t ring_idx(const LzState& s, uint32_t off) {
   return (off + s.align) & kRingMask;
+}
+// explicit shared-space accesses on 32-bit addresses (the generic-pointer form costs 64-bit address
+// arithmetic and generic LD/ST on every byte)
+template <int O = 0>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(O) : "memory");
+  return v;
+}
+template <int O = 0>
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0+%1], %2;" :: "r"(a), "n"(O), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t ring_ld(const LzState& s, uint32_t off) { return lds_u8(s.ring + ring_idx(s, off)); }
+__device__ __forceinline__ void ring_st(const LzState& s, uint32_t off, uint32_t v) { sts_u8(s.ring + ring_idx(s, off), v); }
+template <int O>
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.u8 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(O) : "memory");
+  return v;
 }
 
 // Write ring bytes [s.flushed, upto) to global memory.  Vector stores where the global
@@ -61,17 +86,17 @@ __device__ __forceinline__ void lz_flush(LzState& s, uint32_t upto, int lane) {
   // ragged head up to the next 16-byte boundary (in aligned space)
   uint32_t head = (16u - ((f + s.align) & 15u)) & 15u;
   if (head > upto - f) head = upto - f;
-  if ((uint32_t)lane < head) s.out[f + lane] = s.ring[ring_idx(s, f + lane)];
+  if ((uint32_t)lane < head) s.out[f + lane] = (uint8_t)ring_ld(s, f + lane);
   f += head;
   const uint32_t nvec = (upto - f) >> 4;
   for (uint32_t v = lane; v < nvec; v += kWarp) {
     const uint32_t o = f + (v << 4);
-    const uint4 d = *(const uint4*)(s.ring + ring_idx(s, o));
+    const uint4 d = lds_v4(s.ring + ring_idx(s, o));
     st_v4((uint4*)(s.out + o), d);
   }
   f += nvec << 4;
   const uint32_t tail = upto - f;
-  if ((uint32_t)lane < tail) s.out[f + lane] = s.ring[ring_idx(s, f + lane)];
+  if ((uint32_t)lane < tail) s.out[f + lane] = (uint8_t)ring_ld(s, f + lane);
   s.flushed = upto;
 }
 
@@ -148,8 +173,8 @@ __device__ __forceinline__ void lane_match_copy(const LzState& s, uint32_t ring_
   uint32_t r = 0;                            // source index modulo off (overlapping matches replicate)
   for (uint32_t i = 0; i < M; ++i) {
     const uint32_t sp = src + r;
-    const uint8_t b = (sp >= ring_from) ? s.ring[ring_idx(s, sp)] : s.out[sp];
-    s.ring[ring_idx(s, dst + i)] = b;
+    const uint32_t b = (sp >= ring_from) ? ring_ld(s, sp) : (uint32_t)s.out[sp];
+    ring_st(s, dst + i, b);
     ++r;
     if (r == off) r = 0;
   }
@@ -207,13 +232,13 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
     const uint32_t tO = __shfl_sync(kFull, o_lit, tk);
     const bool tok_ok = (tokmask >> tk) & 1u;
     const uint32_t k = (uint32_t)lane - (uint32_t)tk - 1u;          // literal index within token tk
-    if (tok_ok && lane > tk && k < tL) s.ring[ring_idx(s, tO + k)] = (uint8_t)b0;
+    if (tok_ok && lane > tk && k < tL) ring_st(s, tO + k, b0);
     // literal bytes past the window can only belong to the last token
     const uint32_t lL = __shfl_sync(kFull, t.L, last);
     const uint32_t lO = __shfl_sync(kFull, o_lit, last);
     if ((uint32_t)last + 1u + lL > 32u) {
       const uint32_t k2 = 32u + (uint32_t)lane - (uint32_t)last - 1u;
-      if (k2 < lL) s.ring[ring_idx(s, lO + k2)] = win[32 + lane];
+      if (k2 < lL) ring_st(s, lO + k2, win[32 + lane]);
     }
   }
   // --- matches -------------------------------------------------------------------------------
@@ -235,34 +260,52 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
     const bool in_ring = src0 >= ring_from && sidx <= kRingBytes - 20u;
     const bool far = src0 + t.M <= ring_from;                // flushed long ago: read from global
     const bool simple = has_match && off >= t.M && didx <= kRingBytes - 20u && (in_ring || far);
-    uint8_t* const dp = s.ring + didx;
-    const uint8_t* const sp = far ? (const uint8_t*)(s.out + src0) : (const uint8_t*)(s.ring + sidx);
+    const uint32_t dp = s.ring + didx, sp = s.ring + sidx;
+    const uint8_t* const gp = s.out + src0;
     __syncwarp();
     const int first0 = __ffs(pending) - 1;
     const uint32_t w = __shfl_sync(kFull, o_mat, first0);    // everything below w is final
     const bool ready = has_match && (src_end <= w);
     const bool fast = ready && simple;
-    if (fast) {
-      const uint8_t b0 = sp[0], b1 = sp[1], b2 = sp[2], b3 = sp[3];
-      dp[0] = b0;
-      if (t.M > 1) dp[1] = b1;
-      if (t.M > 2) dp[2] = b2;
-      if (t.M > 3) dp[3] = b3;
+    const bool fast_r = fast && !far, fast_g = fast && far;
+    if (fast_r) {
+      const uint32_t b0 = lds_u8<0>(sp), b1 = lds_u8<1>(sp), b2 = lds_u8<2>(sp), b3 = lds_u8<3>(sp);
+      sts_u8<0>(dp, b0);
+      if (t.M > 1) sts_u8<1>(dp, b1);
+      if (t.M > 2) sts_u8<2>(dp, b2);
+      if (t.M > 3) sts_u8<3>(dp, b3);
     }
-    if (__any_sync(kFull, fast && t.M > 4u)) {
-      if (fast && t.M > 4u) {
-        const uint8_t b0 = sp[4], b1 = sp[5], b2 = sp[6], b3 = sp[7];
-        dp[4] = b0;
-        if (t.M > 5) dp[5] = b1;
-        if (t.M > 6) dp[6] = b2;
-        if (t.M > 7) dp[7] = b3;
+    if (__any_sync(kFull, fast_r && t.M > 4u)) {
+      if (fast_r && t.M > 4u) {
+        const uint32_t b0 = lds_u8<4>(sp), b1 = lds_u8<5>(sp), b2 = lds_u8<6>(sp), b3 = lds_u8<7>(sp);
+        sts_u8<4>(dp, b0);
+        if (t.M > 5) sts_u8<5>(dp, b1);
+        if (t.M > 6) sts_u8<6>(dp, b2);
+        if (t.M > 7) sts_u8<7>(dp, b3);
       }
-      if (__any_sync(kFull, fast && t.M > 8u)) {
-        if (fast && t.M > 8u) {
-#pragma unroll
-          for (uint32_t i = 8; i < 18; ++i)
-            if (i < t.M) dp[i] = sp[i];
+      if (__any_sync(kFull, fast_r && t.M > 8u)) {
+        if (fast_r && t.M > 8u) {
+          if (8 < t.M) sts_u8<8>(dp, lds_u8<8>(sp));
+          if (9 < t.M) sts_u8<9>(dp, lds_u8<9>(sp));
+          if (10 < t.M) sts_u8<10>(dp, lds_u8<10>(sp));
+          if (11 < t.M) sts_u8<11>(dp, lds_u8<11>(sp));
+          if (12 < t.M) sts_u8<12>(dp, lds_u8<12>(sp));
+          if (13 < t.M) sts_u8<13>(dp, lds_u8<13>(sp));
+          if (14 < t.M) sts_u8<14>(dp, lds_u8<14>(sp));
+          if (15 < t.M) sts_u8<15>(dp, lds_u8<15>(sp));
+          if (16 < t.M) sts_u8<16>(dp, lds_u8<16>(sp));
+          if (17 < t.M) sts_u8<17>(dp, lds_u8<17>(sp));
         }
+      }
+    }
+    if (__any_sync(kFull, fast_g)) {
+      // sources flushed long ago: all loads of the lane are issued before the first store
+      if (fast_g) {
+        uint32_t b[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) b[i] = ((uint32_t)i < t.M) ? (uint32_t)gp[i] : 0u;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) if ((uint32_t)i < t.M) sts_u8(dp + i, b[i]);
       }
     }
     pending &= ~__ballot_sync(kFull, fast);
@@ -275,10 +318,13 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
       const uint32_t f_off = f_pack & 0xffffu, f_M = f_pack >> 16;
       if ((uint32_t)lane < f_M) {
         uint32_t r = lane;
-        if (r >= f_off) r %= f_off;                          // overlapping match replicates its period
+        if (r >= f_off) {                                    // overlapping match replicates its period
+          r -= f_off;
+          if (r >= f_off) { r -= f_off; if (r >= f_off) r %= f_off; }
+        }
         const uint32_t q = f_omat - f_off + r;
-        const uint8_t b = (q >= ring_from) ? s.ring[ring_idx(s, q)] : s.out[q];
-        s.ring[ring_idx(s, f_omat + lane)] = b;
+        const uint32_t b = (q >= ring_from) ? ring_ld(s, q) : (uint32_t)s.out[q];
+        ring_st(s, f_omat + lane, b);
       }
       pending &= pending - 1;
     }
@@ -298,7 +344,7 @@ constexpr uint32_t kMediumMax = 192;
 
 __device__ __forceinline__ void ring_put_literals(LzState& s, uint32_t dst, const uint8_t* __restrict__ src,
                                                   uint32_t n, int lane) {
-  for (uint32_t i = lane; i < n; i += kWarp) s.ring[ring_idx(s, dst + i)] = src[i];
+  for (uint32_t i = lane; i < n; i += kWarp) ring_st(s, dst + i, src[i]);
 }
 
 // dst[0..n) = dst[-off..] with LZ77 semantics, all inside the ring (far sources from global).
@@ -311,8 +357,8 @@ __device__ __forceinline__ void ring_match(LzState& s, uint32_t dst, uint32_t of
       const uint32_t j = base + lane;
       if (j < n) {
         const uint32_t sp = src + j;
-        const uint8_t b = (sp >= ring_from) ? s.ring[ring_idx(s, sp)] : s.out[sp];
-        s.ring[ring_idx(s, dst + j)] = b;
+        const uint32_t b = (sp >= ring_from) ? ring_ld(s, sp) : (uint32_t)s.out[sp];
+        ring_st(s, dst + j, b);
       }
       __syncwarp();
     }
@@ -322,8 +368,8 @@ __device__ __forceinline__ void ring_match(LzState& s, uint32_t dst, uint32_t of
     const uint32_t step = 32u % off;
     for (uint32_t j = lane; j < n; j += kWarp) {
       const uint32_t sp = src + r;
-      const uint8_t b = (sp >= ring_from) ? s.ring[ring_idx(s, sp)] : s.out[sp];
-      s.ring[ring_idx(s, dst + j)] = b;
+      const uint32_t b = (sp >= ring_from) ? ring_ld(s, sp) : (uint32_t)s.out[sp];
+      ring_st(s, dst + j, b);
       r += step;
       if (r >= off) r -= off;
     }

@@ -231,7 +231,7 @@ __device__ __forceinline__ bool snappy_decode_chunk_v2(const uint8_t* in, uint32
   s.in = in; s.in_n = in_n; s.out = out; s.out_cap = ulen;
   s.ip = ip; s.op = 0; s.flushed = 0; s.ring_lo = 0;
   s.align = (uint32_t)((uintptr_t)out & 15u);
-  s.ring = ring;
+  s.ring = (uint32_t)__cvta_generic_to_shared(ring);
   if (!lz_decode_stream<SnappyDecode>(s, lane)) return false;
   if (s.op != (uint32_t)ulen) return false;
   *produced = s.op;
