@@ -109,45 +109,9 @@ lz4_decompress_kernel(const void* const* __restrict__ comp_ptrs,
 // v2 decode (lz_decode.cuh): lane-parallel short-token path + this slow path
 // ---------------------------------------------------------------------------
 struct Lz4Decode : Lz4Policy {
-  __device__ static __forceinline__ bool at_end(const LzState&) { return false; }   // ends inside slow_token
-  // one sequence with L + M <= kMediumMax, executed inside the ring
-  __device__ static __forceinline__ int medium_token(LzState& s, int lane) {
-    const uint8_t* __restrict__ in = s.in;
-    const uint32_t in_n = s.in_n;
-    uint32_t ip = s.ip;
-    if (ip >= in_n) return -1;
-    const uint32_t tok = in[ip++];
-    uint32_t ll = tok >> 4;
-    if (ll == 15) { if (!lz4_read_ext(in, in_n, ip, ll, lane)) return -1; }
-    if (ll > in_n - ip) return -1;
-    if (ll > kMediumMax) return 0;
-    const uint32_t lit_at = ip;
-    ip += ll;
-    if (ip >= in_n) {                              // last sequence: literals only
-      if ((uint64_t)ll > s.out_cap - s.op) return -1;
-      ring_put_literals(s, s.op, in + lit_at, ll, lane);
-      s.op += ll; s.ip = ip;
-      return 2;
-    }
-    if (in_n - ip < 2) return -1;
-    const uint32_t off = load_u16(in + ip);
-    ip += 2;
-    uint32_t ml = tok & 15u;
-    if (ml == 15) { if (!lz4_read_ext(in, in_n, ip, ml, lane)) return -1; }
-    ml += 4;
-    if (ll + ml > kMediumMax) return 0;
-    if ((uint64_t)(ll + ml) > s.out_cap - s.op) return -1;
-    if (off == 0 || off > s.op + ll) return -1;
-    const uint32_t rf = ring_from_of(s);
-    ring_put_literals(s, s.op, in + lit_at, ll, lane);
-    __syncwarp();
-    ring_match(s, s.op + ll, off, ml, rf, lane);
-    s.op += ll + ml;
-    s.ip = ip;
-    return 1;
-  }
-  // one full sequence (token, literals, match) on global memory; 2 = final literals consumed
-  __device__ static __forceinline__ int slow_token(LzState& s, int lane) {
+  __device__ static __forceinline__ bool at_end(const LzState&) { return false; }   // ends inside serial_token
+  // one full sequence (token, literals, match), parsed once; 2 = final literals consumed
+  __device__ static __forceinline__ int serial_token(LzState& s, int lane) {
     const uint8_t* __restrict__ in = s.in;
     const uint32_t in_n = s.in_n;
     uint32_t ip = s.ip;
@@ -157,21 +121,23 @@ struct Lz4Decode : Lz4Policy {
     if (ll == 15) { if (!lz4_read_ext(in, in_n, ip, ll, lane)) return -1; }
     if (ll > in_n - ip) return -1;
     if ((uint64_t)ll > s.out_cap - s.op) return -1;
-    if (ll) warp_copy<true>(s.out + s.op, in + ip, ll, lane);
-    ip += ll; s.op += ll;
-    if (ip >= in_n) { s.ip = ip; return 2; }
+    const uint32_t lit_at = ip;
+    ip += ll;
+    if (ip >= in_n) {                              // last sequence: literals only
+      lz_emit_literals(s, in + lit_at, ll, lane);
+      s.ip = ip;
+      return 2;
+    }
     if (in_n - ip < 2) return -1;
     const uint32_t off = load_u16(in + ip);
     ip += 2;
     uint32_t ml = tok & 15u;
     if (ml == 15) { if (!lz4_read_ext(in, in_n, ip, ml, lane)) return -1; }
     ml += 4;
-    if (off == 0 || off > s.op) return -1;
-    if ((uint64_t)ml > s.out_cap - s.op) return -1;
-    __syncwarp();
-    warp_match_copy(s.out + s.op, off, ml, lane);
-    __syncwarp();
-    s.op += ml;
+    if (off == 0 || (uint64_t)off > (uint64_t)s.op + ll) return -1;
+    if ((uint64_t)ml > s.out_cap - s.op - ll) return -1;
+    lz_emit_literals(s, in + lit_at, ll, lane);
+    lz_emit_match(s, off, ml, lane);
     s.ip = ip;
     return 1;
   }
@@ -181,6 +147,11 @@ __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t 
                                                     uint64_t out_cap, uint32_t* produced,
                                                     uint8_t* ring, int lane) {
   if (in_n == 0) { *produced = 0; return true; }
+  // Adaptive strategy: a chunk that compressed >= 4x is dominated by long matches; the ring /
+  // lane-parallel machinery only costs instructions there, so it is decoded by the direct
+  // global-memory token loop (16-byte vector copies).  Dense short-token chunks take the
+  // lane-parallel path.
+  if (out_cap >= 4ull * in_n) return lz4_decode_chunk<true>(in, in_n, out, out_cap, produced, lane);
   LzState s;
   s.in = in; s.in_n = in_n; s.out = out; s.out_cap = out_cap > 0xffffffffull ? 0xffffffffull : out_cap;
   s.ip = 0; s.op = 0; s.flushed = 0; s.ring_lo = 0;
@@ -193,7 +164,8 @@ __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t 
 
 constexpr int kLzDecWarps = 4;
 
-__global__ void __launch_bounds__(kLzDecWarps * 32, 8)
+template <int kMinCtas>
+__global__ void __launch_bounds__(kLzDecWarps * 32, kMinCtas)
 lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
                          const size_t* __restrict__ comp_bytes,
                          const size_t* __restrict__ out_caps,
@@ -206,20 +178,27 @@ lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
   const int w = threadIdx.x >> 5;
   const size_t warp_global = (size_t)blockIdx.x * kLzDecWarps + w;
   const size_t warps_total = (size_t)gridDim.x * kLzDecWarps;
-  WarpTicket sched(ticket, warp_global, warps_total);
-  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
-    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
-    const size_t in_n64 = comp_bytes[c];
-    uint8_t* out = (uint8_t*)out_ptrs[c];
-    const uint64_t cap = (uint64_t)out_caps[c];
-    uint32_t produced = 0;
-    bool ok = in_n64 <= 0xffffffffull;
-    if (ok) ok = lz4_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane);
-    if (lane == 0) {
-      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
-      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
+  // Two passes over the ticket space: dense short-token chunks (compressed < 4x, the expensive
+  // ones) are handed out first, cheap long-match chunks fill the tail -- unequal chunks would
+  // otherwise leave a few warps finishing expensive chunks alone at the end of the batch.
+  for (int pass = 0; pass < 2; ++pass) {
+    WarpTicket sched(ticket ? ticket + pass : nullptr, warp_global, warps_total);
+    for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+      const size_t in_n64 = comp_bytes[c];
+      const uint64_t cap = (uint64_t)out_caps[c];
+      const bool heavy = cap < 4ull * in_n64;
+      if (heavy != (pass == 0)) continue;
+      const uint8_t* in = (const uint8_t*)comp_ptrs[c];
+      uint8_t* out = (uint8_t*)out_ptrs[c];
+      uint32_t produced = 0;
+      bool ok = in_n64 <= 0xffffffffull;
+      if (ok) ok = lz4_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane);
+      if (lane == 0) {
+        if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
+        if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -382,7 +361,7 @@ nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
   unsigned long long* ticket = nullptr;
   if (temp && temp_bytes >= kSchedBytes) {
     ticket = (unsigned long long*)temp;
-    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned long long), stream));
   }
   static const bool use_v1 = getenv("NVCOMP_B200_LZ_V1") != nullptr;   // developer A/B switch
   if (use_v1) {
@@ -390,9 +369,21 @@ nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
     lz4_decompress_kernel<true><<<grid, 128, 0, stream>>>(
         comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
   } else {
-    const int grid = persistent_grid(8, batch, kLzDecWarps);
-    lz4_decompress_v2_kernel<<<grid, kLzDecWarps * 32, 0, stream>>>(
-        comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    static const char* occ_env = getenv("NVCOMP_B200_LZ_OCC");   // developer A/B switch: CTAs per SM
+    const int occ = occ_env ? atoi(occ_env) : 10;   // measured best (profiles/): 40 warps/SM, 48 registers
+    if (occ >= 12) {
+      const int grid = persistent_grid(12, batch, kLzDecWarps);
+      lz4_decompress_v2_kernel<12><<<grid, kLzDecWarps * 32, 0, stream>>>(
+          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    } else if (occ >= 10) {
+      const int grid = persistent_grid(10, batch, kLzDecWarps);
+      lz4_decompress_v2_kernel<10><<<grid, kLzDecWarps * 32, 0, stream>>>(
+          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    } else {
+      const int grid = persistent_grid(8, batch, kLzDecWarps);
+      lz4_decompress_v2_kernel<8><<<grid, kLzDecWarps * 32, 0, stream>>>(
+          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    }
   }
   B200_CUDA_TRY(cudaGetLastError());
   return nvcompSuccess;

@@ -219,9 +219,13 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
   }
   const uint32_t total = __shfl_sync(kFull, incl, 31);
   if ((uint64_t)s.op + total > s.out_cap) return 0;        // let the slow path find the exact error
-  const uint32_t o_lit = s.op + incl - len;
+  // From here on output positions are kept in "aligned space" (offset + s.align): the ring index
+  // is then just (pos & mask) and (s.out - s.align)[pos] is the global address.
+  const uint32_t rbase = s.ring;
+  const uint8_t* const outa = s.out - s.align;
+  const uint32_t o_lit = s.op + s.align + incl - len;
   const uint32_t o_mat = o_lit + t.L;
-  const bool bad = is_tok && t.M && (off == 0u || off > o_mat);
+  const bool bad = is_tok && t.M && (off == 0u || off > o_mat - s.align);
   if (__any_sync(kFull, bad)) return -1;
 
   // --- literals: every window byte finds its token and scatters itself --------------------
@@ -232,13 +236,13 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
     const uint32_t tO = __shfl_sync(kFull, o_lit, tk);
     const bool tok_ok = (tokmask >> tk) & 1u;
     const uint32_t k = (uint32_t)lane - (uint32_t)tk - 1u;          // literal index within token tk
-    if (tok_ok && lane > tk && k < tL) ring_st(s, tO + k, b0);
+    if (tok_ok && lane > tk && k < tL) sts_u8(rbase + ((tO + k) & kRingMask), b0);
     // literal bytes past the window can only belong to the last token
     const uint32_t lL = __shfl_sync(kFull, t.L, last);
     const uint32_t lO = __shfl_sync(kFull, o_lit, last);
     if ((uint32_t)last + 1u + lL > 32u) {
       const uint32_t k2 = 32u + (uint32_t)lane - (uint32_t)last - 1u;
-      if (k2 < lL) ring_st(s, lO + k2, win[32 + lane]);
+      if (k2 < lL) sts_u8(rbase + ((lO + k2) & kRingMask), win[32 + lane]);
     }
   }
   // --- matches -------------------------------------------------------------------------------
@@ -246,68 +250,63 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
   // (they end at or below the output position of the first match of the window): on tabular
   // data that is the majority.  The common case (no overlap, source entirely in the ring or
   // entirely in flushed global memory, no ring wrap-around) is a branch-free unrolled copy in
-  // tiers of 4 bytes with immediate offsets.  The remaining matches depend on output of this
-  // same window and are retired in order, the whole warp copying one match (<= 18 bytes, one
-  // byte per lane) per step.
-  const uint32_t ring_from = max(s.ring_lo, s.op > kRingReach ? s.op - kRingReach : 0u);
+  // tiers with immediate offsets.  The remaining matches depend on output of this same window
+  // and are retired in order, the whole warp copying one match (<= 18 bytes, one byte per
+  // lane) per step.
+  const uint32_t ring_from = max(s.ring_lo, s.op > kRingReach ? s.op - kRingReach : 0u) + s.align;
   const bool has_match = is_tok && t.M != 0u;
   unsigned pending = __ballot_sync(kFull, has_match);
   const uint32_t src0 = o_mat - off;
   const uint32_t pack = off | (t.M << 16);
   if (pending) {
     const uint32_t src_end = src0 + min(t.M, off);           // exclusive end of the bytes this match reads
-    const uint32_t didx = ring_idx(s, o_mat), sidx = ring_idx(s, src0);
+    const uint32_t didx = o_mat & kRingMask, sidx = src0 & kRingMask;
     const bool in_ring = src0 >= ring_from && sidx <= kRingBytes - 20u;
     const bool far = src0 + t.M <= ring_from;                // flushed long ago: read from global
     const bool simple = has_match && off >= t.M && didx <= kRingBytes - 20u && (in_ring || far);
-    const uint32_t dp = s.ring + didx, sp = s.ring + sidx;
-    const uint8_t* const gp = s.out + src0;
+    const uint32_t dp = rbase + didx, sp = rbase + sidx;
+    const uint8_t* const gp = outa + src0;
     __syncwarp();
     const int first0 = __ffs(pending) - 1;
     const uint32_t w = __shfl_sync(kFull, o_mat, first0);    // everything below w is final
     const bool ready = has_match && (src_end <= w);
     const bool fast = ready && simple;
     const bool fast_r = fast && !far, fast_g = fast && far;
-    if (fast_r) {
-      const uint32_t b0 = lds_u8<0>(sp), b1 = lds_u8<1>(sp), b2 = lds_u8<2>(sp), b3 = lds_u8<3>(sp);
-      sts_u8<0>(dp, b0);
-      if (t.M > 1) sts_u8<1>(dp, b1);
-      if (t.M > 2) sts_u8<2>(dp, b2);
-      if (t.M > 3) sts_u8<3>(dp, b3);
+#define B200_TIER4(LD, SRC, A, B, C, D)                                                        \
+    {                                                                                          \
+      const uint32_t x0 = LD<A>(SRC), x1 = LD<B>(SRC), x2 = LD<C>(SRC), x3 = LD<D>(SRC);       \
+      sts_u8<A>(dp, x0);                                                                       \
+      if (t.M > B) sts_u8<B>(dp, x1);                                                          \
+      if (t.M > C) sts_u8<C>(dp, x2);                                                          \
+      if (t.M > D) sts_u8<D>(dp, x3);                                                          \
     }
+#define B200_TAIL10(LD, SRC)                                                                   \
+    {                                                                                          \
+      if (8 < t.M) sts_u8<8>(dp, LD<8>(SRC));    if (9 < t.M) sts_u8<9>(dp, LD<9>(SRC));       \
+      if (10 < t.M) sts_u8<10>(dp, LD<10>(SRC)); if (11 < t.M) sts_u8<11>(dp, LD<11>(SRC));    \
+      if (12 < t.M) sts_u8<12>(dp, LD<12>(SRC)); if (13 < t.M) sts_u8<13>(dp, LD<13>(SRC));    \
+      if (14 < t.M) sts_u8<14>(dp, LD<14>(SRC)); if (15 < t.M) sts_u8<15>(dp, LD<15>(SRC));    \
+      if (16 < t.M) sts_u8<16>(dp, LD<16>(SRC)); if (17 < t.M) sts_u8<17>(dp, LD<17>(SRC));    \
+    }
+    if (fast_r) B200_TIER4(lds_u8, sp, 0, 1, 2, 3)
     if (__any_sync(kFull, fast_r && t.M > 4u)) {
-      if (fast_r && t.M > 4u) {
-        const uint32_t b0 = lds_u8<4>(sp), b1 = lds_u8<5>(sp), b2 = lds_u8<6>(sp), b3 = lds_u8<7>(sp);
-        sts_u8<4>(dp, b0);
-        if (t.M > 5) sts_u8<5>(dp, b1);
-        if (t.M > 6) sts_u8<6>(dp, b2);
-        if (t.M > 7) sts_u8<7>(dp, b3);
-      }
+      if (fast_r && t.M > 4u) B200_TIER4(lds_u8, sp, 4, 5, 6, 7)
       if (__any_sync(kFull, fast_r && t.M > 8u)) {
-        if (fast_r && t.M > 8u) {
-          if (8 < t.M) sts_u8<8>(dp, lds_u8<8>(sp));
-          if (9 < t.M) sts_u8<9>(dp, lds_u8<9>(sp));
-          if (10 < t.M) sts_u8<10>(dp, lds_u8<10>(sp));
-          if (11 < t.M) sts_u8<11>(dp, lds_u8<11>(sp));
-          if (12 < t.M) sts_u8<12>(dp, lds_u8<12>(sp));
-          if (13 < t.M) sts_u8<13>(dp, lds_u8<13>(sp));
-          if (14 < t.M) sts_u8<14>(dp, lds_u8<14>(sp));
-          if (15 < t.M) sts_u8<15>(dp, lds_u8<15>(sp));
-          if (16 < t.M) sts_u8<16>(dp, lds_u8<16>(sp));
-          if (17 < t.M) sts_u8<17>(dp, lds_u8<17>(sp));
-        }
+        if (fast_r && t.M > 8u) B200_TAIL10(lds_u8, sp)
       }
     }
     if (__any_sync(kFull, fast_g)) {
-      // sources flushed long ago: all loads of the lane are issued before the first store
-      if (fast_g) {
-        uint32_t b[18];
-#pragma unroll
-        for (int i = 0; i < 18; ++i) b[i] = ((uint32_t)i < t.M) ? (uint32_t)gp[i] : 0u;
-#pragma unroll
-        for (int i = 0; i < 18; ++i) if ((uint32_t)i < t.M) sts_u8(dp + i, b[i]);
+      // sources flushed long ago (read from global memory), same tiers
+      if (fast_g) B200_TIER4(ldg_u8, gp, 0, 1, 2, 3)
+      if (__any_sync(kFull, fast_g && t.M > 4u)) {
+        if (fast_g && t.M > 4u) B200_TIER4(ldg_u8, gp, 4, 5, 6, 7)
+        if (__any_sync(kFull, fast_g && t.M > 8u)) {
+          if (fast_g && t.M > 8u) B200_TAIL10(ldg_u8, gp)
+        }
       }
     }
+#undef B200_TIER4
+#undef B200_TAIL10
     pending &= ~__ballot_sync(kFull, fast);
     // in-order retirement of everything else
     while (pending) {
@@ -323,8 +322,8 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
           if (r >= f_off) { r -= f_off; if (r >= f_off) r %= f_off; }
         }
         const uint32_t q = f_omat - f_off + r;
-        const uint32_t b = (q >= ring_from) ? ring_ld(s, q) : (uint32_t)s.out[q];
-        ring_st(s, f_omat + lane, b);
+        const uint32_t b = (q >= ring_from) ? lds_u8(rbase + (q & kRingMask)) : (uint32_t)outa[q];
+        sts_u8(rbase + ((f_omat + lane) & kRingMask), b);
       }
       pending &= pending - 1;
     }
@@ -380,34 +379,94 @@ __device__ __forceinline__ uint32_t ring_from_of(const LzState& s) {
   return max(s.ring_lo, s.op > kRingReach ? s.op - kRingReach : 0u);
 }
 
-// Decode driver shared by LZ4 and Snappy.  P::slow_token(s, lane) executes exactly one token
-// at s.ip directly on global memory (ring already flushed) and returns 1 (continue),
-// 2 (stream finished) or -1 (malformed).
+// one already-produced output byte, wherever it currently lives
+__device__ __forceinline__ uint32_t lz_out_byte(const LzState& s, uint32_t pos, uint32_t ring_from) {
+  return (pos >= ring_from) ? ring_ld(s, pos) : (uint32_t)s.out[pos];
+}
+
+// ---------------------------------------------------------------------------
+// Serial (one token at a time, whole warp) emitters for tokens the lane-parallel path cannot
+// take.  Up to kMediumMax bytes stay inside the ring; longer runs go straight to global
+// memory as 16-byte vectors and the ring restarts empty behind them.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void lz_emit_literals(LzState& s, const uint8_t* __restrict__ src, uint32_t n, int lane) {
+  if (n <= kMediumMax) {
+    ring_put_literals(s, s.op, src, n, lane);
+    s.op += n;
+    return;
+  }
+  lz_flush(s, s.op, lane);
+  warp_copy<true>(s.out + s.op, src, n, lane);
+  s.op += n;
+  s.flushed = s.op;
+  s.ring_lo = s.op;
+}
+
+__device__ __forceinline__ void lz_emit_match(LzState& s, uint32_t off, uint32_t n, int lane) {
+  __syncwarp();
+  if (n <= kMediumMax) {
+    ring_match(s, s.op, off, n, ring_from_of(s), lane);
+    s.op += n;
+    return;
+  }
+  const uint32_t dst = s.op;
+  if (off <= 16u && (off & (off - 1u)) == 0u) {
+    // Long run with a period that divides 16 (typed run-length data).  Every 16-byte aligned
+    // vector of the run is the same: build it once in registers from the period bytes (ring or
+    // global), no store->load round trip, then stream it out with vector stores.
+    const uint32_t rf = ring_from_of(s);
+    const uint32_t src = dst - off, m = off - 1u;
+    const uint32_t head = (16u - ((dst + s.align) & 15u)) & 15u;
+    uint32_t wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc |= lz_out_byte(s, src + ((head + 4u * q + i) & m), rf) << (8 * i);
+      wv[q] = acc;
+    }
+    const uint32_t hb = lz_out_byte(s, src + ((uint32_t)lane & m), rf);
+    lz_flush(s, dst, lane);                                   // everything before the run is now in global memory
+    uint8_t* o = s.out + dst;
+    if ((uint32_t)lane < head) o[lane] = (uint8_t)hb;
+    const uint32_t nvec = (n - head) >> 4;
+    uint4* d16 = (uint4*)(o + head);
+    const uint4 pat = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    for (uint32_t v = lane; v < nvec; v += kWarp) st_v4(d16 + v, pat);
+    const uint32_t j = head + (nvec << 4) + lane;             // < 16 tail bytes
+    if (j < n) {
+      const uint32_t k = (j - head) & 15u;                    // position inside the pattern vector
+      const uint32_t q = k >> 2;
+      const uint32_t wsel = q == 0 ? wv[0] : q == 1 ? wv[1] : q == 2 ? wv[2] : wv[3];
+      o[j] = (uint8_t)(wsel >> (8 * (k & 3u)));
+    }
+  } else {
+    lz_flush(s, dst, lane);
+    __syncwarp();
+    warp_match_copy(s.out + dst, off, n, lane);
+  }
+  __syncwarp();
+  s.op += n;
+  s.flushed = s.op;
+  s.ring_lo = s.op;
+}
+
+// Decode driver shared by LZ4 and Snappy.  P::serial_token(s, lane) executes exactly one token
+// at s.ip with the emitters above and returns 1 (continue), 2 (stream finished) or -1 (malformed).
 template <class P>
 __device__ __forceinline__ bool lz_decode_stream(LzState& s, int lane) {
   while (true) {
     if (P::at_end(s)) break;
-    // a token that needs the medium / long path is recognised from its first byte: do not pay for
-    // a speculative window parse that would retire nothing
+    // a token that needs the serial path is recognised from its first byte: do not pay for a
+    // speculative window parse that would retire nothing
     if (s.ip + P::kLook <= s.in_n && !P::is_stop(s.in[s.ip])) {
       const int r = lz_fast_iter<P>(s, lane);
       if (r < 0) return false;
       if (r > 0) { lz_flush_blocks(s, lane); continue; }
     }
-    {
-      // P::medium_token: 1 = token executed inside the ring, 2 = stream finished,
-      // 0 = token too long (falls through to the global-memory path), -1 = malformed
-      const int m = P::medium_token(s, lane);
-      if (m < 0) return false;
-      if (m == 1) { lz_flush_blocks(s, lane); continue; }
-      if (m == 2) break;
-    }
-    lz_flush(s, s.op, lane);
-    __syncwarp();
-    const int r = P::slow_token(s, lane);
+    const int r = P::serial_token(s, lane);
     if (r < 0) return false;
-    s.flushed = s.op;
-    s.ring_lo = s.op;
+    lz_flush_blocks(s, lane);
     if (r == 2) break;
   }
   lz_flush(s, s.op, lane);

@@ -67,6 +67,22 @@ __device__ __forceinline__ bool snappy_decode_chunk(const uint8_t* __restrict__ 
       len = (tag >> 2) + 1;
       off = load_u16(in + ip);
       ip += 2;
+      // a run of copy-2 elements with the same offset is one long match (64 bytes per element):
+      // lane i inspects element i, the run is merged and copied once
+      const uint32_t q = ip + 3u * (uint32_t)lane;
+      uint32_t flen = 0;
+      bool same = false;
+      if (q + 3u <= in_n) {
+        const uint32_t t2 = in[q];
+        same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
+        flen = (t2 >> 2) + 1;
+      }
+      const unsigned m = __ballot_sync(kFull, same);
+      const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
+      uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
+      if (len <= n_out - op && add <= n_out - op - len) { len += add; ip += 3u * nf; }
     } else {
       if (in_n - ip < 4) return false;
       len = (tag >> 2) + 1;
@@ -118,58 +134,9 @@ snappy_decompress_kernel(const void* const* __restrict__ comp_ptrs,
 // ---------------------------------------------------------------------------
 struct SnappyDecode : SnappyPolicy {
   __device__ static __forceinline__ bool at_end(const LzState& s) { return s.ip >= s.in_n; }
-  // one element with length <= kMediumMax, executed inside the ring
-  __device__ static __forceinline__ int medium_token(LzState& s, int lane) {
-    const uint8_t* __restrict__ in = s.in;
-    const uint32_t in_n = s.in_n;
-    uint32_t ip = s.ip;
-    const uint32_t n_out = (uint32_t)s.out_cap;
-    const uint32_t tag = in[ip++];
-    const uint32_t kind = tag & 3u;
-    uint32_t len, off;
-    if (kind == 0) {
-      len = (tag >> 2) + 1;
-      if (len > 60) {
-        const uint32_t nb = len - 60;
-        if (nb > 2) return 0;                       // >= 64 KB literal: global path
-        if (in_n - ip < nb) return -1;
-        uint32_t v = 0;
-        for (uint32_t i = 0; i < nb; ++i) v |= (uint32_t)in[ip + i] << (8 * i);
-        ip += nb;
-        len = v + 1;
-      }
-      if (len > kMediumMax) return 0;
-      if (len > in_n - ip || len > n_out - s.op) return -1;
-      ring_put_literals(s, s.op, in + ip, len, lane);
-      s.ip = ip + len;
-      s.op += len;
-      return 1;
-    }
-    if (kind == 1) {
-      if (ip >= in_n) return -1;
-      len = 4 + ((tag >> 2) & 7u);
-      off = ((tag >> 5) << 8) | in[ip++];
-    } else if (kind == 2) {
-      if (in_n - ip < 2) return -1;
-      len = (tag >> 2) + 1;
-      off = load_u16(in + ip);
-      ip += 2;
-    } else {
-      if (in_n - ip < 4) return -1;
-      len = (tag >> 2) + 1;
-      off = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8) | ((uint32_t)in[ip + 2] << 16)
-            | ((uint32_t)in[ip + 3] << 24);
-      ip += 4;
-    }
-    if (off == 0 || off > s.op || len > n_out - s.op) return -1;
-    __syncwarp();
-    ring_match(s, s.op, off, len, ring_from_of(s), lane);
-    s.op += len;
-    s.ip = ip;
-    return 1;
-  }
-  // one element (literal or copy) on global memory
-  __device__ static __forceinline__ int slow_token(LzState& s, int lane) {
+  // one element (literal or copy).  A run of copy-2 elements with the same offset -- how Snappy
+  // spells one long match (64 bytes per element) -- is merged and emitted as a single match.
+  __device__ static __forceinline__ int serial_token(LzState& s, int lane) {
     const uint8_t* __restrict__ in = s.in;
     const uint32_t in_n = s.in_n;
     uint32_t ip = s.ip;
@@ -189,9 +156,8 @@ struct SnappyDecode : SnappyPolicy {
         len = v + 1;
       }
       if (len > in_n - ip || len > n_out - s.op) return -1;
-      warp_copy<true>(s.out + s.op, in + ip, len, lane);
+      lz_emit_literals(s, in + ip, len, lane);
       s.ip = ip + len;
-      s.op += len;
       return 1;
     }
     if (kind == 1) {
@@ -203,6 +169,21 @@ struct SnappyDecode : SnappyPolicy {
       len = (tag >> 2) + 1;
       off = load_u16(in + ip);
       ip += 2;
+      // merge following copy-2 elements with the same offset (lane i inspects element i)
+      const uint32_t q = ip + 3u * (uint32_t)lane;
+      uint32_t flen = 0;
+      bool same = false;
+      if (q + 3u <= in_n) {
+        const uint32_t t2 = in[q];
+        same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
+        flen = (t2 >> 2) + 1;
+      }
+      const unsigned m = __ballot_sync(kFull, same);
+      const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
+      uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
+      if (add <= n_out - s.op - min(len, n_out - s.op)) { len += add; ip += 3u * nf; }
     } else {
       if (in_n - ip < 4) return -1;
       len = (tag >> 2) + 1;
@@ -211,10 +192,7 @@ struct SnappyDecode : SnappyPolicy {
       ip += 4;
     }
     if (off == 0 || off > s.op || len > n_out - s.op) return -1;
-    __syncwarp();
-    warp_match_copy(s.out + s.op, off, len, lane);
-    __syncwarp();
-    s.op += len;
+    lz_emit_match(s, off, len, lane);
     s.ip = ip;
     return 1;
   }
@@ -227,6 +205,9 @@ __device__ __forceinline__ bool snappy_decode_chunk_v2(const uint8_t* in, uint32
   uint64_t ulen;
   if (!snappy_read_preamble(in, in_n, ip, ulen)) return false;
   if (ulen > out_cap) return false;
+  // Adaptive strategy (see lz4.cu): chunks that compressed >= 4x are long-match dominated and
+  // take the direct global-memory token loop.
+  if (ulen >= 4ull * in_n) return snappy_decode_chunk(in, in_n, out, out_cap, produced, lane);
   LzState s;
   s.in = in; s.in_n = in_n; s.out = out; s.out_cap = ulen;
   s.ip = ip; s.op = 0; s.flushed = 0; s.ring_lo = 0;
@@ -240,7 +221,8 @@ __device__ __forceinline__ bool snappy_decode_chunk_v2(const uint8_t* in, uint32
 
 constexpr int kLzDecWarps = 4;
 
-__global__ void __launch_bounds__(kLzDecWarps * 32, 8)
+template <int kMinCtas>
+__global__ void __launch_bounds__(kLzDecWarps * 32, kMinCtas)
 snappy_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
                             const size_t* __restrict__ comp_bytes,
                             const size_t* __restrict__ out_caps,
@@ -253,107 +235,30 @@ snappy_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
   const int w = threadIdx.x >> 5;
   const size_t warp_global = (size_t)blockIdx.x * kLzDecWarps + w;
   const size_t warps_total = (size_t)gridDim.x * kLzDecWarps;
-  WarpTicket sched(ticket, warp_global, warps_total);
-  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
-    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
-    const size_t in_n64 = comp_bytes[c];
-    uint8_t* out = (uint8_t*)out_ptrs[c];
-    const uint64_t cap = (uint64_t)out_caps[c];
-    uint32_t produced = 0;
-    bool ok = in_n64 <= 0xffffffffull;
-    if (ok) ok = snappy_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane);
-    if (lane == 0) {
-      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
-      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
-    }
-    __syncwarp();
-  }
-}
-
-
-// ---------------------------------------------------------------------------
-// EXPERIMENT (NVCOMP_B200_LZ_TPC=1): one THREAD per chunk, scalar decode straight on global
-// memory.  Token-heavy tabular chunks are bounded by warp-instructions per token; a scalar
-// decoder retires 32 tokens (of 32 different chunks) per warp instruction at the price of
-// uncoalesced accesses.  Used to measure that trade-off.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ bool snappy_decode_thread(const uint8_t* __restrict__ in, uint32_t in_n,
-                                                     uint8_t* out, uint64_t out_cap, uint32_t* produced) {
-  uint32_t ip = 0;
-  uint64_t ulen = 0;
-  uint32_t shift = 0;
-  while (true) {
-    if (ip >= in_n || shift > 28) return false;
-    const uint32_t b = in[ip++];
-    ulen |= (uint64_t)(b & 0x7fu) << shift;
-    if (!(b & 0x80u)) break;
-    shift += 7;
-  }
-  if (ulen > out_cap || ulen > 0xffffffffull) return false;
-  const uint32_t n_out = (uint32_t)ulen;
-  uint32_t op = 0;
-  while (ip < in_n) {
-    const uint32_t tag = in[ip++];
-    const uint32_t kind = tag & 3u;
-    uint32_t len, off;
-    if (kind == 0) {
-      len = (tag >> 2) + 1;
-      if (len > 60) {
-        const uint32_t nb = len - 60;
-        if (in_n - ip < nb) return false;
-        uint32_t v = 0;
-        for (uint32_t i = 0; i < nb; ++i) v |= (uint32_t)in[ip + i] << (8 * i);
-        ip += nb;
-        if (v == 0xffffffffu) return false;
-        len = v + 1;
+  // Two passes over the ticket space: dense short-token chunks (compressed < 4x, the expensive
+  // ones) are handed out first, cheap long-match chunks fill the tail -- unequal chunks would
+  // otherwise leave a few warps finishing expensive chunks alone at the end of the batch.
+  for (int pass = 0; pass < 2; ++pass) {
+    WarpTicket sched(ticket ? ticket + pass : nullptr, warp_global, warps_total);
+    for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+      const size_t in_n64 = comp_bytes[c];
+      const uint64_t cap = (uint64_t)out_caps[c];
+      const bool heavy = cap < 4ull * in_n64;
+      if (heavy != (pass == 0)) continue;
+      const uint8_t* in = (const uint8_t*)comp_ptrs[c];
+      uint8_t* out = (uint8_t*)out_ptrs[c];
+      uint32_t produced = 0;
+      bool ok = in_n64 <= 0xffffffffull;
+      if (ok) ok = snappy_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane);
+      if (lane == 0) {
+        if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
+        if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
       }
-      if (len > in_n - ip || len > n_out - op) return false;
-      for (uint32_t i = 0; i < len; ++i) out[op + i] = in[ip + i];
-      ip += len; op += len;
-      continue;
+      __syncwarp();
     }
-    if (kind == 1) {
-      if (ip >= in_n) return false;
-      len = 4 + ((tag >> 2) & 7u);
-      off = ((tag >> 5) << 8) | in[ip++];
-    } else if (kind == 2) {
-      if (in_n - ip < 2) return false;
-      len = (tag >> 2) + 1;
-      off = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);
-      ip += 2;
-    } else {
-      if (in_n - ip < 4) return false;
-      len = (tag >> 2) + 1;
-      off = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8) | ((uint32_t)in[ip + 2] << 16)
-            | ((uint32_t)in[ip + 3] << 24);
-      ip += 4;
-    }
-    if (off == 0 || off > op || len > n_out - op) return false;
-    const uint8_t* src = out + op - off;
-    uint8_t* dst = out + op;
-    for (uint32_t i = 0; i < len; ++i) dst[i] = src[i];
-    op += len;
   }
-  if (op != n_out) return false;
-  *produced = op;
-  return true;
 }
 
-__global__ void __launch_bounds__(64)
-snappy_decompress_tpc_kernel(const void* const* __restrict__ comp_ptrs,
-                             const size_t* __restrict__ comp_bytes,
-                             const size_t* __restrict__ out_caps,
-                             size_t* actual_bytes, size_t batch,
-                             void* const* __restrict__ out_ptrs,
-                             nvcompStatus_t* statuses) {
-  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= batch) return;
-  uint32_t produced = 0;
-  const bool ok = snappy_decode_thread((const uint8_t*)comp_ptrs[c], (uint32_t)comp_bytes[c],
-                                       (uint8_t*)out_ptrs[c], out_caps[c], &produced);
-  if (actual_bytes) actual_bytes[c] = ok ? produced : 0;
-  if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
-}
 
 // Size query: only the varint preamble is read (one thread per chunk).
 __global__ void snappy_size_kernel(const void* const* __restrict__ comp_ptrs,
@@ -546,21 +451,29 @@ nvcompStatus_t nvcompBatchedSnappyDecompressAsync(
   unsigned long long* ticket = nullptr;
   if (temp && temp_bytes >= kSchedBytes) {
     ticket = (unsigned long long*)temp;
-    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned long long), stream));
   }
   static const bool use_v1 = getenv("NVCOMP_B200_LZ_V1") != nullptr;   // developer A/B switch
-  static const bool use_tpc = getenv("NVCOMP_B200_LZ_TPC") != nullptr; // developer experiment
-  if (use_tpc) {
-    snappy_decompress_tpc_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, stream>>>(
-        comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses);
-  } else if (use_v1) {
+  if (use_v1) {
     const int grid = persistent_grid(10, batch, 4);
     snappy_decompress_kernel<<<grid, 128, 0, stream>>>(
         comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
   } else {
-    const int grid = persistent_grid(8, batch, kLzDecWarps);
-    snappy_decompress_v2_kernel<<<grid, kLzDecWarps * 32, 0, stream>>>(
-        comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    static const char* occ_env = getenv("NVCOMP_B200_LZ_OCC");   // developer A/B switch: CTAs per SM
+    const int occ = occ_env ? atoi(occ_env) : 10;   // measured best (profiles/): 40 warps/SM, 48 registers
+    if (occ >= 12) {
+      const int grid = persistent_grid(12, batch, kLzDecWarps);
+      snappy_decompress_v2_kernel<12><<<grid, kLzDecWarps * 32, 0, stream>>>(
+          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    } else if (occ >= 10) {
+      const int grid = persistent_grid(10, batch, kLzDecWarps);
+      snappy_decompress_v2_kernel<10><<<grid, kLzDecWarps * 32, 0, stream>>>(
+          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    } else {
+      const int grid = persistent_grid(8, batch, kLzDecWarps);
+      snappy_decompress_v2_kernel<8><<<grid, kLzDecWarps * 32, 0, stream>>>(
+          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+    }
   }
   B200_CUDA_TRY(cudaGetLastError());
   return nvcompSuccess;
