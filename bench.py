@@ -36,6 +36,9 @@ FMT = {"lz4": "LZ4", "snappy": "Snappy", "cascaded": "Cascaded", "bitcomp": "Bit
 ORACLE_ID = {"lz4": 0, "snappy": 1, "cascaded": 2, "bitcomp": 3, "ans": 4}
 DEFAULT_DATASET = {"lz4": "lz4_mixed", "snappy": "tabular_f32", "cascaded": "sorted_i64",
                    "bitcomp": "sorted_i64", "ans": "lowentropy_bytes"}
+KERNEL_NAME = {"lz4": "lz4_decompress_v2_kernel<10>", "snappy": "snappy_decompress_v2_kernel<10>",
+               "cascaded": "cascaded_decompress_kernel", "bitcomp": "bitcomp_decompress_kernel",
+               "ans": "ans_decompress_kernel"}
 WORKLOAD_NAME = {
     "snappy": "BASELINE configs[1]: Snappy batched decompress, 10000x64KB synthetic tabular float32 chunks per GPU",
     "lz4": "BASELINE configs[4] per-GPU share: LZ4 batched decompress, 10000x64KB chunks (run-length int32 + tabular float32) per GPU",
@@ -76,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -240,6 +243,9 @@ def run_gpu(args):
         codec.decompress_async(comp.ptrs.data_ptr(), comp.sizes.data_ptr(), caps.data_ptr(), actual.data_ptr(), n,
                                temp.data_ptr(), tb, out.ptrs.data_ptr(), status.data_ptr(), sh)
 
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()          # sampled from the warm-up on: same kernel, same load as the timed region
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -247,9 +253,6 @@ def run_gpu(args):
     assert bool((status == 0).all().item()) and bool((actual == CHUNK).all().item()), "decompress status/size"
     assert torch.equal(out.slab[:total], inp.slab[:total]), "decompressed bytes differ from the input"
 
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -275,10 +278,21 @@ def run_gpu(args):
         comp_total_all = float(cs.item())
     else:
         comp_total_all = float(comp_total)
+    if rank == 0:
+        # the timed region lasts only tens of ms; keep the identical load running (untimed) until the
+        # sampler has seen ~0.6 s of it, so the clock record describes this kernel under load
+        t_load = time.time()
+        while time.time() - t_load < 0.6:
+            for _ in range(10):
+                step()
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + 0.6 s of the same launches (untimed), nvidia-smi -lms 20"
 
     # ---- e2e: host buffers in, host buffers out, through the same C-ABI call, pipelined in slices
     e2e = run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world)
+    e2e_dev = run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world, copy_back=False)
 
     ms_per_step = elapsed_ms / args.steps
     value = world * total / (ms_per_step * 1e-3) / 1e9
@@ -302,11 +316,12 @@ def run_gpu(args):
                                 f"{(total + comp_total) / 1e6:.0f} MB vs 126 MB L2)",
                    "sharding": "contiguous chunk range per rank, no data-path collective" if world > 1 else "single GPU"},
         "e2e": e2e,
+        "e2e_device_consumer": e2e_dev,
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": f"{kind}_decompress_kernel", "avg_launch_ms": round(avg_launch_ms, 4)},
+                     "kernel": KERNEL_NAME[kind], "avg_launch_ms": round(avg_launch_ms, 4)},
         "clocks": clocks,
     }
     if distribute is not None:
@@ -321,7 +336,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world):
+def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world, copy_back=True):
     """Same decode through the C ABI, but the compressed chunks start in pinned HOST memory and the
     decompressed chunks end in pinned HOST memory; both copies are inside the timed region.  The batch is
     processed in slices on three streams so H2D, decode and D2H overlap."""
@@ -342,9 +357,11 @@ def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world):
     actual = torch.zeros(n, dtype=torch.int64, device=dev)
     status = torch.full((n,), -1, dtype=torch.int32, device=dev)
     h_status = torch.empty(n, dtype=torch.int32).pin_memory()
-    nslices = 8
+    nslices = 4
     bounds = [n * i // nslices for i in range(nslices + 1)]
-    s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    # one stream per slice: H2D -> decode -> D2H in order on that stream; the slices' copies share the
+    # two copy engines and their decode kernels overlap (a quarter batch does not fill the GPU)
+    streams = [torch.cuda.Stream() for _ in range(nslices)]
     tb = codec.decompress_get_temp_size(n, CHUNK)
     temps = [torch.empty(max(tb, 1), dtype=torch.uint8, device=dev) for _ in range(nslices)]
 
@@ -352,26 +369,25 @@ def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world):
         for i in range(nslices):
             a, b = bounds[i], bounds[i + 1]
             lo, hi = int(c_offs[a]), int(c_offs[b - 1] + c_sizes[b - 1])
-            with torch.cuda.stream(s_in):
+            st = streams[i]
+            with torch.cuda.stream(st):
                 d_comp[lo:hi].copy_(h_comp[lo:hi], non_blocking=True)
-                ev_in = torch.cuda.Event(); ev_in.record(s_in)
-            s_k.wait_event(ev_in)
-            with torch.cuda.stream(s_k):
                 codec.decompress_async(ptrs.data_ptr() + 8 * a, sizes.data_ptr() + 8 * a, caps.data_ptr() + 8 * a,
                                        actual.data_ptr() + 8 * a, b - a, temps[i].data_ptr(), tb,
-                                       out.ptrs.data_ptr() + 8 * a, status.data_ptr() + 4 * a, s_k.cuda_stream)
-                ev_k = torch.cuda.Event(); ev_k.record(s_k)
-            s_out.wait_event(ev_k)
-            with torch.cuda.stream(s_out):
-                h_out[a * CHUNK: b * CHUNK].copy_(out.slab[a * CHUNK: b * CHUNK], non_blocking=True)
-        with torch.cuda.stream(s_out):
-            h_status.copy_(status, non_blocking=True)
+                                       out.ptrs.data_ptr() + 8 * a, status.data_ptr() + 4 * a, st.cuda_stream)
+                if copy_back:
+                    h_out[a * CHUNK: b * CHUNK].copy_(out.slab[a * CHUNK: b * CHUNK], non_blocking=True)
+                h_status[a:b].copy_(status[a:b], non_blocking=True)
+
+    def drain():
+        for st in streams:
+            st.synchronize()
 
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-    ok = bool((h_status == 0).all().item()) and np.array_equal(
-        h_out.numpy()[: 4 * CHUNK], inp.slab[: 4 * CHUNK].cpu().numpy())
+    ok = bool((h_status == 0).all().item()) and (not copy_back or np.array_equal(
+        h_out.numpy()[: 4 * CHUNK], inp.slab[: 4 * CHUNK].cpu().numpy()))
     assert ok, "e2e output mismatch"
     if world > 1:
         dist.barrier()
@@ -381,8 +397,7 @@ def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world):
     e0.record()
     for _ in range(steps):
         step()
-        s_out.synchronize()
-    torch.cuda.current_stream().wait_stream(s_out)
+        drain()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -390,11 +405,16 @@ def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if not copy_back:
+        return {"value": round(world * total / (ms * 1e-3) / 1e9, 2), "unit": "GB/s",
+                "h2d_bytes_per_step": comp_total, "d2h_bytes_per_step": 4 * n, "ms_per_step": round(ms, 3),
+                "what": "same call, decompressed chunks stay in HBM for a GPU consumer; only statuses return"}
     return {"value": round(world * total / (ms * 1e-3) / 1e9, 2), "unit": "GB/s",
             "h2d_bytes_per_step": comp_total, "d2h_bytes_per_step": total + 4 * n,
-            "ms_per_step": round(ms, 3), "pipeline": f"{nslices} slices on 3 streams (H2D | decode | D2H)",
+            "ms_per_step": round(ms, 3), "pipeline": f"{nslices} slices, one stream each (H2D -> decode -> D2H)",
             "what": "pinned host compressed chunks -> H2D -> nvcompBatched*DecompressAsync -> D2H of the "
-                    "decompressed chunks and statuses into pinned host memory"}
+                    "decompressed chunks and statuses into pinned host memory (PCIe-bound: "
+                    "d2h_bytes/ms_per_step is the link rate)"}
 
 
 def run_reference(args):

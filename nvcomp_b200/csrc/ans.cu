@@ -106,15 +106,14 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
       }
       __syncthreads();
       if (!s_fail) {
-        // fill the LUT slot-parallel: binary search of the cumulative table (8 steps)
-        for (uint32_t slot = threadIdx.x; slot < kAnsM; slot += kAnsThreads) {
-          uint32_t lo = 0;
-#pragma unroll
-          for (uint32_t step = 128; step; step >>= 1)
-            if (s_cum[lo + step] <= slot) lo += step;
-          const uint32_t c0 = s_cum[lo], f = s_cum[lo + 1] - c0;
+        // fill the LUT: warp w owns symbols w, w+4, ...; its lanes stride over the symbol's slots
+        // (no dependent search chains: two table reads per symbol, then independent stores)
+        for (uint32_t sym = w; sym < 256; sym += kAnsWarps) {
+          const uint32_t c0 = s_cum[sym], c1 = s_cum[sym + 1];
+          const uint32_t f = c1 - c0;
           if (f > 4095u) s_fail = 1;
-          s_lut[slot] = lo | ((f & 0xfffu) << 8) | ((slot - c0) << 20);
+          const uint32_t base = sym | ((f & 0xfffu) << 8);
+          for (uint32_t slot = c0 + lane; slot < c1; slot += kWarp) s_lut[slot] = base | ((slot - c0) << 20);
         }
       }
       __syncthreads();

@@ -30,13 +30,14 @@
 namespace b200 {
 
 constexpr uint32_t kCascMagic = 0x31435343u;  // "CSC1"
-constexpr int kCascWarps = 4;
+constexpr int kCascWarps = 8;        // decode CTA: 8 warps, one partition each (4- and 8-byte elements)
+constexpr int kCascCompWarps = 4;    // compress CTA
 constexpr uint32_t kCascFastPart = 4096;      // partitions up to this size: one warp each
 constexpr uint32_t kCascMaxPart = 16384;
-// per-warp shared memory: A, B value buffers (P bytes each) + run/idx u16 arrays
-// sized for 1-byte elements (2*P each) = 6*P.
-constexpr uint32_t kCascSmemPerWarp = 6 * kCascFastPart;
-constexpr uint32_t kCascSmem = kCascWarps * kCascSmemPerWarp;   // 96 KB = 6 * kCascMaxPart
+// per-warp shared memory of the decoder: A, B value buffers (P bytes each) + run-start and run-index
+// u16 arrays (2 * P/TS bytes each) = 2P + 4P/TS.  The CTA owns 96 KB: 8 warps x 12 KB for 4- and
+// 8-byte elements, 4 warps x 24 KB for 1- and 2-byte elements, 1 warp x 96 KB for partitions > 4 KB.
+constexpr uint32_t kCascSmem = 96 * 1024;
 
 __host__ __device__ inline uint32_t casc_type_size(int t) {
   switch (t) {
@@ -119,9 +120,9 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
   using T = typename Elem<TS>::T;
   T* bufA = (T*)sm;
   T* bufB = (T*)(sm + P);
-  uint16_t* runs = (uint16_t*)(sm + 2 * P);
-  uint16_t* idx = (uint16_t*)(sm + 4 * P);
   const uint32_t cap = P / TS;
+  uint16_t* runs = (uint16_t*)(sm + 2 * P);
+  uint16_t* idx = (uint16_t*)(sm + 2 * P + 2 * cap);
   if (n_out > cap) return false;
 
   // walk stream headers
@@ -284,9 +285,10 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
     if (ok) {
       const uint32_t* part_off = (const uint32_t*)(in + 20);
       const bool fast = h.part_bytes <= kCascFastPart;
-      const int nw = fast ? kCascWarps : 1;
-      uint8_t* sm = fast ? smem + (size_t)w * kCascSmemPerWarp : smem;
+      const uint32_t ts0 = casc_type_size(h.type);
+      const int nw = fast ? (ts0 >= 4 ? 8 : 4) : 1;
       const uint32_t P = fast ? kCascFastPart : kCascMaxPart;
+      uint8_t* sm = smem + (size_t)w * (kCascSmem / nw);
       if (w < nw) {
         for (uint32_t p = w; p < h.num_parts; p += nw) {
           const uint32_t o0 = part_off[p], o1 = part_off[p + 1];
@@ -459,7 +461,7 @@ __device__ uint32_t casc_encode_part(const uint8_t* __restrict__ in, uint32_t n,
 
 constexpr uint32_t kCascCompSmemPerWarp(uint32_t P) { return 4 * P + 64 + 2 * P + 64; }
 
-__global__ void __launch_bounds__(kCascWarps * 32)
+__global__ void __launch_bounds__(kCascCompWarps * 32)
 cascaded_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* __restrict__ in_bytes,
                          size_t batch, void* const* __restrict__ out_ptrs, size_t* out_bytes,
                          nvcompBatchedCascadedOpts_t opts, uint32_t smem_per_warp,
@@ -575,7 +577,7 @@ nvcompStatus_t nvcompBatchedCascadedCompressAsync(
   }
   const uint32_t per_warp = (kCascCompSmemPerWarp((uint32_t)opts.chunk_size) + 15u) & ~15u;
   int nw = (int)((220u * 1024u) / per_warp);
-  if (nw > kCascWarps) nw = kCascWarps;
+  if (nw > kCascCompWarps) nw = kCascCompWarps;
   if (nw < 1) return nvcompErrorInvalidValue;
   const size_t smem = (size_t)nw * per_warp;
   static bool attr_set = false;

@@ -11,6 +11,8 @@ long oracle_cascaded_decompress(const uint8_t* src, size_t n, uint8_t* dst, size
 long oracle_bitcomp_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) __attribute__((weak));
 long oracle_ans_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) __attribute__((weak));
 
+static pthread_barrier_t g_start;
+
 typedef struct {
   int codec;
   const uint8_t* comp;
@@ -21,11 +23,14 @@ typedef struct {
   size_t stride;
   size_t* out_len;
   int failed;
+  struct timespec t_start, t_end;   /* stamped by the worker itself, after the start barrier */
 } job_t;
 
 static void* worker(void* p)
 {
   job_t* j = (job_t*)p;
+  pthread_barrier_wait(&g_start);   /* timing starts when every thread is up (spawn cost excluded) */
+  clock_gettime(CLOCK_MONOTONIC, &j->t_start);
   for (size_t i = j->begin; i < j->end; ++i) {
     long r = -1;
     const uint8_t* s = j->comp + j->off[i];
@@ -41,6 +46,7 @@ static void* worker(void* p)
     if (r < 0) { j->failed = 1; r = 0; }
     if (j->out_len) j->out_len[i] = (size_t)r;
   }
+  clock_gettime(CLOCK_MONOTONIC, &j->t_end);
   return 0;
 }
 
@@ -53,15 +59,22 @@ double oracle_batch_decompress(int codec, const uint8_t* comp, const size_t* com
   pthread_t th[256];
   job_t jobs[256];
   struct timespec t0, t1;
-  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_barrier_init(&g_start, 0, (unsigned)nthreads + 1);
   for (int t = 0; t < nthreads; ++t) {
     jobs[t] = (job_t){codec, comp, comp_off, comp_len, count * t / nthreads, count * (t + 1) / nthreads,
-                      out, out_stride, out_len, 0};
+                      out, out_stride, out_len, 0, {0, 0}, {0, 0}};
     pthread_create(&th[t], 0, worker, &jobs[t]);
   }
+  pthread_barrier_wait(&g_start);
   int failed = 0;
   for (int t = 0; t < nthreads; ++t) { pthread_join(th[t], 0); failed |= jobs[t].failed; }
-  clock_gettime(CLOCK_MONOTONIC, &t1);
+  /* elapsed = last worker finish - first worker start (the caller thread may be descheduled) */
+  t0 = jobs[0].t_start; t1 = jobs[0].t_end;
+  for (int t = 1; t < nthreads; ++t) {
+    if (jobs[t].t_start.tv_sec < t0.tv_sec || (jobs[t].t_start.tv_sec == t0.tv_sec && jobs[t].t_start.tv_nsec < t0.tv_nsec)) t0 = jobs[t].t_start;
+    if (jobs[t].t_end.tv_sec > t1.tv_sec || (jobs[t].t_end.tv_sec == t1.tv_sec && jobs[t].t_end.tv_nsec > t1.tv_nsec)) t1 = jobs[t].t_end;
+  }
+  pthread_barrier_destroy(&g_start);
   double s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
   return failed ? -s : s;
 }
