@@ -77,6 +77,8 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     const size_t in_bytes = comp_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in));      // LDG/STG instead of generic LD/ST
+    __builtin_assume(__isGlobal(out));
     AnsHeader h;
     bool ok = ans_read_header(in, in_bytes, h);
     if (ok && h.n > out_caps[c]) ok = false;
@@ -126,27 +128,39 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
             const uint32_t begin = sg * kAnsSeg;
             const uint32_t ns = min(kAnsSeg, h.n - begin);
             uint32_t x = ((const uint32_t*)(in + o0))[lane];
-            const uint16_t* words = (const uint16_t*)(in + o0 + 128);
+            const uint16_t* __restrict__ words = (const uint16_t*)(in + o0 + 128);
             const uint32_t nwords = (o1 - o0 - 128u) >> 1;
             uint32_t wpos = 0;
-            uint8_t* o = out + begin;
-            const uint32_t rounds = (ns + 31) >> 5;
-            for (uint32_t r = 0; r < rounds; ++r) {
-              const uint32_t i = (r << 5) + lane;
-              const bool active = i < ns;
+            uint8_t* o = out + begin + lane;
+            const unsigned lt = (1u << lane) - 1u;
+            // full rounds: every lane decodes one symbol; straight-line, the only predicated
+            // instruction is the renormalisation word load
+            const uint32_t full = ns >> 5;
+            for (uint32_t r = 0; r < full; ++r) {
+              const uint32_t e = s_lut[x & (kAnsM - 1)];
+              o[r << 5] = (uint8_t)e;
+              x = ((e >> 8) & 0xfffu) * (x >> kAnsLog) + (e >> 20);
+              const bool need = x < kAnsLow;
+              const unsigned m = __ballot_sync(kFull, need);
+              const uint32_t idx = wpos + __popc(m & lt);
+              uint32_t wd = 0;
+              if (need && idx < nwords) wd = words[idx];
+              x = need ? ((x << 16) | wd) : x;
+              wpos += __popc(m);
+            }
+            // tail round (ns % 32 symbols)
+            if (ns & 31u) {
+              const bool active = (uint32_t)lane < (ns & 31u);
               bool need = false;
               if (active) {
                 const uint32_t e = s_lut[x & (kAnsM - 1)];
-                o[i] = (uint8_t)e;
+                o[full << 5] = (uint8_t)e;
                 x = ((e >> 8) & 0xfffu) * (x >> kAnsLog) + (e >> 20);
                 need = x < kAnsLow;
               }
               const unsigned m = __ballot_sync(kFull, need);
-              if (need) {
-                const uint32_t idx = wpos + __popc(m & ((1u << lane) - 1u));
-                const uint32_t wd = (idx < nwords) ? (uint32_t)words[idx] : 0u;
-                x = (x << 16) | wd;
-              }
+              const uint32_t idx = wpos + __popc(m & lt);
+              if (need) x = (x << 16) | ((idx < nwords) ? (uint32_t)words[idx] : 0u);
               wpos += __popc(m);
             }
             // integrity: the stream must be consumed exactly and all states return to L
@@ -374,6 +388,7 @@ nvcompStatus_t nvcompBatchedANSCompressAsync(
     const void* const* in_ptrs, const size_t* in_bytes, size_t max_chunk, size_t batch,
     void* temp, size_t temp_bytes, void* const* out_ptrs, size_t* out_bytes,
     nvcompBatchedANSOpts_t opts, cudaStream_t stream) {
+  log_call("nvcompBatchedANSCompressAsync", batch, max_chunk, stream);
   if (opts.type != nvcomp_rANS) return nvcompErrorInvalidValue;
   if (max_chunk > nvcompANSCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
   if (batch == 0) return nvcompSuccess;
@@ -404,6 +419,7 @@ nvcompStatus_t nvcompBatchedANSDecompressGetTempSizeEx(size_t n, size_t m, size_
 nvcompStatus_t nvcompBatchedANSGetDecompressSizeAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, size_t* out_sizes,
     size_t batch, cudaStream_t stream) {
+  log_call("nvcompBatchedANSGetDecompressSizeAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
   ans_size_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(comp_ptrs, comp_bytes, out_sizes, batch);
@@ -415,6 +431,7 @@ nvcompStatus_t nvcompBatchedANSDecompressAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, const size_t* out_caps,
     size_t* actual_bytes, size_t batch, void* const temp, size_t temp_bytes,
     void* const* out_ptrs, nvcompStatus_t* statuses, cudaStream_t stream) {
+  log_call("nvcompBatchedANSDecompressAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
   unsigned long long* ticket = nullptr;

@@ -121,11 +121,33 @@ __device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const 
     const uint32_t bits = desc & 0xffu;
     const uint64_t first = p64[0];
     uint64_t sum = 0;
+    if (bits <= 16u) {
+      // the lane's four values span at most 64 + 63 bits: two word loads, then shifts
+      // (bits is uniform over the block, so this branch does not diverge)
+      const uint32_t bitpos = 4u * (uint32_t)lane * bits;
+      const uint32_t w0 = bitpos >> 6, s0 = bitpos & 63u;
+      uint64_t lo = 0, hi = 0;
+      if (bits) {
+        lo = p64[1 + w0];
+        if (s0 + 4u * bits > 64u) hi = p64[2 + w0];
+      }
+      const uint64_t mask = (1ull << bits) - 1ull;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint64_t z = bits ? btc_unpack(p64 + 1, 4 * lane + j, bits) : 0ull;
-      sum += btc_unzigzag(z);
-      v[j] = sum;
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t sj = s0 + (uint32_t)j * bits;          // < 128
+        uint64_t z;
+        if (sj < 64u) z = (lo >> sj) | (sj ? (hi << (64u - sj)) : 0ull);
+        else z = hi >> (sj - 64u);
+        sum += btc_unzigzag(z & mask);
+        v[j] = sum;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t z = btc_unpack(p64 + 1, 4 * lane + j, bits);
+        sum += btc_unzigzag(z);
+        v[j] = sum;
+      }
     }
     uint64_t incl = sum;
 #pragma unroll
@@ -185,6 +207,7 @@ bitcomp_decompress_kernel(const void* const* __restrict__ comp_ptrs,
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     const size_t in_bytes = comp_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
     BtcHeader h;
     bool ok = btc_read_header(in, in_bytes, h);
     const uint32_t ts = ok ? btc_type_size(h.type) : 1;
@@ -383,6 +406,7 @@ bitcomp_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* _
     const uint8_t* in = (const uint8_t*)in_ptrs[c];
     const uint32_t n_bytes = (uint32_t)in_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
     const uint32_t n_elems = n_bytes / ts;
     const uint32_t nblocks = (n_elems + kBtcBlock - 1) / kBtcBlock;
     if (threadIdx.x == 0) {
@@ -483,6 +507,7 @@ nvcompStatus_t nvcompBatchedBitcompCompressAsync(
     const void* const* in_ptrs, const size_t* in_bytes, size_t max_chunk, size_t batch,
     void* temp, size_t temp_bytes, void* const* out_ptrs, size_t* out_bytes,
     nvcompBatchedBitcompFormatOpts opts, cudaStream_t stream) {
+  log_call("nvcompBatchedBitcompCompressAsync", batch, max_chunk, stream);
   const nvcompStatus_t st = btc_check_opts(opts);
   if (st != nvcompSuccess) return st;
   if (max_chunk > nvcompBitcompCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
@@ -513,6 +538,7 @@ nvcompStatus_t nvcompBatchedBitcompDecompressGetTempSizeEx(size_t n, size_t m, s
 nvcompStatus_t nvcompBatchedBitcompGetDecompressSizeAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, size_t* out_sizes,
     size_t batch, cudaStream_t stream) {
+  log_call("nvcompBatchedBitcompGetDecompressSizeAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
   bitcomp_size_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(comp_ptrs, comp_bytes, out_sizes, batch);
@@ -524,6 +550,7 @@ nvcompStatus_t nvcompBatchedBitcompDecompressAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, const size_t* out_caps,
     size_t* actual_bytes, size_t batch, void* const temp, size_t temp_bytes,
     void* const* out_ptrs, nvcompStatus_t* statuses, cudaStream_t stream) {
+  log_call("nvcompBatchedBitcompDecompressAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
   unsigned long long* ticket = nullptr;

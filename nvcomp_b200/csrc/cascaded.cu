@@ -30,13 +30,14 @@
 namespace b200 {
 
 constexpr uint32_t kCascMagic = 0x31435343u;  // "CSC1"
-constexpr int kCascWarps = 8;        // decode CTA: 8 warps, one partition each (4- and 8-byte elements)
+constexpr int kCascWarps = 16;       // decode CTA: up to 16 warps, one partition each
 constexpr int kCascCompWarps = 4;    // compress CTA
 constexpr uint32_t kCascFastPart = 4096;      // partitions up to this size: one warp each
 constexpr uint32_t kCascMaxPart = 16384;
-// per-warp shared memory of the decoder: A, B value buffers (P bytes each) + run-start and run-index
-// u16 arrays (2 * P/TS bytes each) = 2P + 4P/TS.  The CTA owns 96 KB: 8 warps x 12 KB for 4- and
-// 8-byte elements, 4 warps x 24 KB for 1- and 2-byte elements, 1 warp x 96 KB for partitions > 4 KB.
+// per-warp shared memory of the decoder: one value buffer (P bytes; two when more than one layer pair
+// is configured) + a run-index u16 array (2 * P/TS bytes).  The CTA owns 96 KB and activates as many
+// warps (<= 16) as fit: 16 for 4/8-byte elements with one layer pair and 4 KB partitions, ... 1 for a
+// 16 KB partition of 1-byte elements.
 constexpr uint32_t kCascSmem = 96 * 1024;
 
 __host__ __device__ inline uint32_t casc_type_size(int t) {
@@ -110,19 +111,20 @@ __host__ __device__ inline uint32_t stream_bytes(uint32_t count, uint32_t bits) 
 
 // ---------------------------------------------------------------------------
 // Decode one partition with one warp.  `n_out` elements expected.
-// sm layout (per warp): A [P] | B [P] | runs u16[P] | idx u16[P]
+// sm layout (per warp): A [P] | (B [P] when two_bufs) | idx u16[P/TS]
+// Delta layers are undone in place; the outermost run-length expansion writes straight to the
+// output (global memory), so the common one-layer configurations need a single value buffer.
 // Returns false on a malformed partition.
 // ---------------------------------------------------------------------------
 template <int TS>
 __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t payload_bytes,
                                  uint8_t* out, uint32_t n_out, int R, int D,
-                                 uint8_t* sm, uint32_t P, int lane) {
+                                 uint8_t* sm, uint32_t P, bool two_bufs, int lane) {
   using T = typename Elem<TS>::T;
   T* bufA = (T*)sm;
-  T* bufB = (T*)(sm + P);
+  T* bufB = (T*)(sm + P);                    // only valid when two_bufs
   const uint32_t cap = P / TS;
-  uint16_t* runs = (uint16_t*)(sm + 2 * P);
-  uint16_t* idx = (uint16_t*)(sm + 2 * P + 2 * cap);
+  uint16_t* idx = (uint16_t*)(sm + (two_bufs ? 2u : 1u) * P);
   if (n_out > cap) return false;
 
   // walk stream headers
@@ -162,63 +164,72 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
   for (uint32_t k = lane; k < count; k += kWarp) bufA[k] = (T)unpack_at(vwords, k, vh.bits, vh.minv);
   __syncwarp();
   T* cur = bufA;
-  T* nxt = bufB;
   const int L = R > D ? R : D;
   for (int i = L - 1; i >= 0; --i) {
     if (i < D) {
-      // undo delta i: cur holds count deltas, result = count+1 values (or the
-      // layer saw an empty list: cin == 0 and nothing to do)
+      // undo delta i in place: cur[0..count) deltas -> cur[0..count] values (shifted by one; the
+      // next tile is loaded before this tile's stores).  cin == 0: the layer saw an empty list.
       const uint32_t c_in = cin[i];
       if (c_in == 0 && count != 0) return false;
       if (c_in != 0) {
-      if (c_in != count + 1 || c_in > cap) return false;
-      uint64_t carry = firsts[i];
-      if (lane == 0) nxt[0] = (T)carry;
-      for (uint32_t base = 0; base < count; base += kWarp) {
-        const uint32_t k = base + lane;
-        uint64_t v = (k < count) ? (uint64_t)cur[k] : 0ull;
-        v = warp_incl_scan_u64(v, lane) + carry;
-        if (k < count) nxt[k + 1] = (T)v;
-        carry = __shfl_sync(kFull, v, 31);
-      }
-      count += 1;
-      __syncwarp();
-      T* t = cur; cur = nxt; nxt = t;
+        if (c_in != count + 1 || c_in > cap) return false;
+        uint64_t carry = firsts[i];
+        uint64_t vnext = ((uint32_t)lane < count) ? (uint64_t)cur[lane] : 0ull;
+        __syncwarp();
+        if (lane == 0) cur[0] = (T)carry;
+        for (uint32_t base = 0; base < count; base += kWarp) {
+          const uint32_t k = base + lane;
+          uint64_t v = vnext;
+          vnext = (k + kWarp < count) ? (uint64_t)cur[k + kWarp] : 0ull;
+          __syncwarp();
+          v = warp_incl_scan_u64(v, lane) + carry;
+          if (k < count) cur[k + 1] = (T)v;
+          carry = __shfl_sync(kFull, v, 31);
+        }
+        count += 1;
+        __syncwarp();
       }
     }
     if (i < R) {
       // expand with runs_i: cur holds `count` values, runs_i holds `count` lengths
       const StreamHdr rh = run_hdr[i];
       if (rh.count != count) return false;
+      const bool last = (i == 0);
+      if (!last && !two_bufs) return false;                  // cannot happen: one buffer only when L == 1
+      T* dst = last ? (T*)out : (cur == bufA ? bufB : bufA);
       const uint64_t* rwords = (const uint64_t*)(payload + run_off[i]);
-      // starts = exclusive scan of run lengths
+      // head flags: idx[start of run k] = k, zero elsewhere
+      {
+        uint32_t* z = (uint32_t*)idx;
+        for (uint32_t j = lane; j < (cap + 1) / 2; j += kWarp) z[j] = 0u;
+      }
+      __syncwarp();
       uint32_t carry = 0;
       for (uint32_t base = 0; base < count; base += kWarp) {
         const uint32_t k = base + lane;
         const uint32_t len = (k < count) ? (uint32_t)unpack_at(rwords, k, rh.bits, rh.minv) : 0u;
         const uint32_t incl = warp_incl_scan_u32(len, lane) + carry;
-        if (k < count) runs[k] = (uint16_t)min(incl - len, 0xffffu);
         carry = __shfl_sync(kFull, incl, 31);
         if (carry > cap) return false;
+        if (k < count && len != 0u) idx[incl - len] = (uint16_t)k;
       }
       const uint32_t total = carry;
       if (total > cap || total < count) return false;
-      // head flags -> run index per output element via max-scan
-      for (uint32_t j = lane; j < total; j += kWarp) idx[j] = 0;
+      if (last && total != n_out) return false;
       __syncwarp();
-      for (uint32_t k = lane; k < count; k += kWarp) idx[runs[k]] = (uint16_t)k;
-      __syncwarp();
+      // run index per output element via max-scan, then gather
       uint32_t mcarry = 0;
       for (uint32_t base = 0; base < total; base += kWarp) {
         const uint32_t j = base + lane;
         uint32_t r = (j < total) ? (uint32_t)idx[j] : 0u;
         r = max(warp_incl_max_u32(r, lane), mcarry);
-        if (j < total) nxt[j] = cur[r];
+        if (j < total) dst[j] = cur[r];
         mcarry = __shfl_sync(kFull, r, 31);
       }
+      if (last) return true;
       count = total;
       __syncwarp();
-      T* t = cur; cur = nxt; nxt = t;
+      cur = dst;
     }
   }
   if (count != n_out) return false;
@@ -252,7 +263,7 @@ __device__ __forceinline__ bool casc_read_header(const uint8_t* in, size_t in_by
   return true;
 }
 
-__global__ void __launch_bounds__(kCascWarps * 32)
+__global__ void __launch_bounds__(kCascWarps * 32, 2)
 cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
                            const size_t* __restrict__ comp_bytes,
                            const size_t* __restrict__ out_caps,
@@ -278,17 +289,20 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     const size_t in_bytes = comp_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
     const size_t cap = out_caps[c];
     CascHeader h;
     bool ok = casc_read_header(in, in_bytes, h);
     if (ok && (h.uncompressed > cap || ((uintptr_t)out & (casc_type_size(h.type) - 1)))) ok = false;
     if (ok) {
       const uint32_t* part_off = (const uint32_t*)(in + 20);
-      const bool fast = h.part_bytes <= kCascFastPart;
       const uint32_t ts0 = casc_type_size(h.type);
-      const int nw = fast ? (ts0 >= 4 ? 8 : 4) : 1;
-      const uint32_t P = fast ? kCascFastPart : kCascMaxPart;
-      uint8_t* sm = smem + (size_t)w * (kCascSmem / nw);
+      const uint32_t P = h.part_bytes;
+      const bool two_bufs = (h.R > h.D ? h.R : h.D) > 1;
+      const uint32_t need = ((two_bufs ? 2u : 1u) * P + 2u * (P / ts0) + 4u + 15u) & ~15u;
+      int nw = (int)(kCascSmem / need);
+      if (nw > kCascWarps) nw = kCascWarps;
+      uint8_t* sm = smem + (size_t)w * need;
       if (w < nw) {
         for (uint32_t p = w; p < h.num_parts; p += nw) {
           const uint32_t o0 = part_off[p], o1 = part_off[p + 1];
@@ -298,10 +312,10 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
             const uint32_t nbytes = min(h.part_bytes, h.uncompressed - begin);
             const uint32_t ts = casc_type_size(h.type);
             switch (ts) {
-              case 1: pok = casc_decode_part<1>(in + o0, o1 - o0, out + begin, nbytes, h.R, h.D, sm, P, lane); break;
-              case 2: pok = casc_decode_part<2>(in + o0, o1 - o0, out + begin, nbytes / 2, h.R, h.D, sm, P, lane); break;
-              case 4: pok = casc_decode_part<4>(in + o0, o1 - o0, out + begin, nbytes / 4, h.R, h.D, sm, P, lane); break;
-              default: pok = casc_decode_part<8>(in + o0, o1 - o0, out + begin, nbytes / 8, h.R, h.D, sm, P, lane); break;
+              case 1: pok = casc_decode_part<1>(in + o0, o1 - o0, out + begin, nbytes, h.R, h.D, sm, P, two_bufs, lane); break;
+              case 2: pok = casc_decode_part<2>(in + o0, o1 - o0, out + begin, nbytes / 2, h.R, h.D, sm, P, two_bufs, lane); break;
+              case 4: pok = casc_decode_part<4>(in + o0, o1 - o0, out + begin, nbytes / 4, h.R, h.D, sm, P, two_bufs, lane); break;
+              default: pok = casc_decode_part<8>(in + o0, o1 - o0, out + begin, nbytes / 8, h.R, h.D, sm, P, two_bufs, lane); break;
             }
           }
           if (!pok && lane == 0) s_fail = 1;
@@ -479,6 +493,7 @@ cascaded_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* 
     const uint8_t* in = (const uint8_t*)in_ptrs[c];
     const uint32_t n = (uint32_t)in_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
     const uint32_t num_parts = (n + P - 1) / P;
     if (lane == 0) {
       uint32_t* hw = (uint32_t*)out;
@@ -565,6 +580,7 @@ nvcompStatus_t nvcompBatchedCascadedCompressAsync(
     const void* const* in_ptrs, const size_t* in_bytes, size_t max_chunk, size_t batch,
     void* temp, size_t temp_bytes, void* const* out_ptrs, size_t* out_bytes,
     nvcompBatchedCascadedOpts_t opts, cudaStream_t stream) {
+  log_call("nvcompBatchedCascadedCompressAsync", batch, max_chunk, stream);
   const nvcompStatus_t st = casc_check_opts(opts);
   if (st != nvcompSuccess) return st;
   if (max_chunk > nvcompCascadedCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
@@ -607,6 +623,7 @@ nvcompStatus_t nvcompBatchedCascadedDecompressGetTempSizeEx(size_t n, size_t m, 
 nvcompStatus_t nvcompBatchedCascadedGetDecompressSizeAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, size_t* out_sizes,
     size_t batch, cudaStream_t stream) {
+  log_call("nvcompBatchedCascadedGetDecompressSizeAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
   cascaded_size_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(comp_ptrs, comp_bytes, out_sizes, batch);
@@ -618,6 +635,7 @@ nvcompStatus_t nvcompBatchedCascadedDecompressAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, const size_t* out_caps,
     size_t* actual_bytes, size_t batch, void* const temp, size_t temp_bytes,
     void* const* out_ptrs, nvcompStatus_t* statuses, cudaStream_t stream) {
+  log_call("nvcompBatchedCascadedDecompressAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
   unsigned long long* ticket = nullptr;

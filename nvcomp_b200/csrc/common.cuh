@@ -223,6 +223,13 @@ inline int persistent_grid(int ctas_per_sm, size_t work_items, int work_per_cta)
   return (int)(g == 0 ? 1 : g);
 }
 
+// call logging (log.cu): NVCOMP_LOG_LEVEL >= 3 logs every low-level API call
+int log_level();
+void log_call(const char* fn, size_t batch, size_t max_chunk, const void* stream);
+
+}  // namespace b200
+namespace b200 {
+
 #define B200_CUDA_TRY(expr)                                  \
   do {                                                       \
     cudaError_t _e = (expr);                                 \

@@ -190,6 +190,7 @@ lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
       if (heavy != (pass == 0)) continue;
       const uint8_t* in = (const uint8_t*)comp_ptrs[c];
       uint8_t* out = (uint8_t*)out_ptrs[c];
+      __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
       uint32_t produced = 0;
       bool ok = in_n64 <= 0xffffffffull;
       if (ok) ok = lz4_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane);
@@ -304,6 +305,7 @@ nvcompStatus_t nvcompBatchedLZ4CompressAsync(
     const void* const* in_ptrs, const size_t* in_bytes, size_t max_chunk, size_t batch,
     void* temp, size_t temp_bytes, void* const* out_ptrs, size_t* out_bytes,
     nvcompBatchedLZ4Opts_t opts, cudaStream_t stream) {
+  log_call("nvcompBatchedLZ4CompressAsync", batch, max_chunk, stream);
   bool ok; const uint32_t step = lz4_step_for(opts.data_type, &ok);
   if (!ok) return nvcompErrorInvalidValue;
   if (max_chunk > nvcompLZ4CompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
@@ -343,6 +345,7 @@ nvcompStatus_t nvcompBatchedLZ4DecompressGetTempSizeEx(
 nvcompStatus_t nvcompBatchedLZ4GetDecompressSizeAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, size_t* out_sizes,
     size_t batch, cudaStream_t stream) {
+  log_call("nvcompBatchedLZ4GetDecompressSizeAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
   const int grid = persistent_grid(8, batch, 4);
@@ -356,6 +359,7 @@ nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, const size_t* out_caps,
     size_t* actual_bytes, size_t batch, void* const temp, size_t temp_bytes,
     void* const* out_ptrs, nvcompStatus_t* statuses, cudaStream_t stream) {
+  log_call("nvcompBatchedLZ4DecompressAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
   unsigned long long* ticket = nullptr;

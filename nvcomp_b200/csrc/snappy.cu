@@ -117,6 +117,7 @@ snappy_decompress_kernel(const void* const* __restrict__ comp_ptrs,
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     const size_t in_n64 = comp_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
     const uint64_t cap = (uint64_t)out_caps[c];
     uint32_t produced = 0;
     bool ok = in_n64 <= 0xffffffffull;
@@ -247,6 +248,7 @@ snappy_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
       if (heavy != (pass == 0)) continue;
       const uint8_t* in = (const uint8_t*)comp_ptrs[c];
       uint8_t* out = (uint8_t*)out_ptrs[c];
+      __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
       uint32_t produced = 0;
       bool ok = in_n64 <= 0xffffffffull;
       if (ok) ok = snappy_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane);
@@ -398,6 +400,7 @@ nvcompStatus_t nvcompBatchedSnappyCompressAsync(
     const void* const* in_ptrs, const size_t* in_bytes, size_t max_chunk, size_t batch,
     void* temp, size_t temp_bytes, void* const* out_ptrs, size_t* out_bytes,
     nvcompBatchedSnappyOpts_t, cudaStream_t stream) {
+  log_call("nvcompBatchedSnappyCompressAsync", batch, max_chunk, stream);
   if (max_chunk > nvcompSnappyCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
   if (batch == 0) return nvcompSuccess;
   if (!in_ptrs || !in_bytes || !out_ptrs || !out_bytes) return nvcompErrorInvalidValue;
@@ -433,6 +436,7 @@ nvcompStatus_t nvcompBatchedSnappyDecompressGetTempSizeEx(size_t n, size_t m, si
 nvcompStatus_t nvcompBatchedSnappyGetDecompressSizeAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, size_t* out_sizes,
     size_t batch, cudaStream_t stream) {
+  log_call("nvcompBatchedSnappyGetDecompressSizeAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
   const int threads = 128;
@@ -446,6 +450,7 @@ nvcompStatus_t nvcompBatchedSnappyDecompressAsync(
     const void* const* comp_ptrs, const size_t* comp_bytes, const size_t* out_caps,
     size_t* actual_bytes, size_t batch, void* const temp, size_t temp_bytes,
     void* const* out_ptrs, nvcompStatus_t* statuses, cudaStream_t stream) {
+  log_call("nvcompBatchedSnappyDecompressAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
   unsigned long long* ticket = nullptr;

@@ -51,3 +51,16 @@ def test_no_cpu_fallback_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in txt and "oracle_" not in txt, os.path.join(dirpath, f)
+
+
+def test_call_logging_env(tmp_path):
+    """NVCOMP_LOG_LEVEL=3 logs every low-level call to NVCOMP_LOG_FILE (reference README.md:79-88)."""
+    import subprocess
+    import sys
+    log = tmp_path / "nv.log"
+    code = ("from nvcomp_b200.batched import Codec\n"
+            "c = Codec('Snappy')\n"
+            "c.decompress_async(None, None, None, None, 0, None, 0, None, None, None)\n")
+    env = dict(os.environ, NVCOMP_LOG_LEVEL="3", NVCOMP_LOG_FILE=str(log), PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=ROOT)
+    assert "nvcompBatchedSnappyDecompressAsync(batch_size=0" in log.read_text()
