@@ -85,40 +85,54 @@ __device__ __forceinline__ void lz77_compress_chunk(
         }
       }
     }
-    const unsigned m = __ballot_sync(kFull, is_match);
-    // Insert only the positions this round consumes (up to and including the match
-    // position): later positions are probed again next round and must still find
-    // their older candidate, not themselves.
-    const int first = m ? __ffs(m) - 1 : 31;
-    if (valid && lane <= first) table[h] = (uint16_t)p;
-    __syncwarp();
+    unsigned m = __ballot_sync(kFull, is_match);
     if (m == 0) {
+      if (valid) table[h] = (uint16_t)p;
+      __syncwarp();
       pos += 32u * step * accel;
       if (misses < 64) ++misses;
       continue;
     }
     misses = 0;
-    const uint32_t mp = __shfl_sync(kFull, p, first);
-    const uint32_t mc = __shfl_sync(kFull, cpos, first);
-    // cooperative forward extension
-    uint32_t len = 4;
-    const uint32_t max_len = match_end_limit - mp;   // mp + len <= match_end_limit
-    while (len < max_len) {
-      const uint32_t j = len + lane;
-      const bool differs = (j >= max_len) || (in[mp + j] != in[mc + j]);
-      const unsigned d = __ballot_sync(kFull, differs);
-      if (d) { len += __ffs(d) - 1; break; }
-      len += 32;
+    // Every verified candidate of this round stays valid, so the round emits as many matches as fit
+    // left to right (greedy): after a match ends, the next candidate at or beyond its end is taken
+    // without re-hashing.  Hash entries are inserted for the positions a match consumes up to its
+    // start; positions beyond the last match are probed again next round.
+    const uint32_t stride = step * accel;
+    int prev_first = -1;
+    uint32_t new_pos = pos;
+    while (m) {
+      const int first = __ffs(m) - 1;
+      const uint32_t mp = __shfl_sync(kFull, p, first);
+      const uint32_t mc = __shfl_sync(kFull, cpos, first);
+      // cooperative forward extension
+      uint32_t len = 4;
+      const uint32_t max_len = match_end_limit - mp;   // mp + len <= match_end_limit
+      while (len < max_len) {
+        const uint32_t j = len + lane;
+        const bool differs = (j >= max_len) || (in[mp + j] != in[mc + j]);
+        const unsigned d = __ballot_sync(kFull, differs);
+        if (d) { len += __ffs(d) - 1; break; }
+        len += 32;
+      }
+      if (len > max_len) len = max_len;
+      if (step > 1) len &= ~(step - 1);   // keep candidate positions element-aligned
+      if (valid && lane > prev_first && lane <= first) table[h] = (uint16_t)p;
+      prev_first = first;
+      if (len < 4) {                       // too short after limits: not a match after all
+        m &= ~(1u << first);
+        if (new_pos <= mp) new_pos = mp + step;
+        continue;
+      }
+      em.sequence(in + anchor, mp - anchor, mp - mc, len, lane);
+      new_pos = mp + len;
+      anchor = new_pos;
+      const uint32_t skip = (new_pos - pos + stride - 1) / stride;   // lanes whose position is consumed
+      if (skip >= 32u) break;
+      m &= ~((1u << skip) - 1u);
     }
-    if (len > max_len) len = max_len;
-    if (step > 1) len &= ~(step - 1);   // keep candidate positions element-aligned
-    if (len < 4) {                       // too short after limits: treat as miss
-      pos = mp + step;
-      continue;
-    }
-    em.sequence(in + anchor, mp - anchor, mp - mc, len, lane);
-    pos = mp + len;
-    anchor = pos;
+    __syncwarp();
+    pos = (new_pos > pos) ? new_pos : pos + 32u * stride;
   }
   em.finish(in + anchor, n - anchor, lane);
 }
