@@ -27,6 +27,7 @@ constexpr int kBtcWarps = 4;
 constexpr int kBtcThreads = kBtcWarps * 32;
 constexpr uint32_t kBtcBlock = 128;          // elements per block
 constexpr uint32_t kBtcTile = 512;           // blocks per offset tile (4 per thread)
+constexpr uint32_t kBtcStage = 12288;        // bytes of packed payload staged per tile by one TMA bulk copy
 
 __host__ __device__ inline uint32_t btc_type_size(int t) {
   switch (t) {
@@ -192,8 +193,17 @@ bitcomp_decompress_kernel(const void* const* __restrict__ comp_ptrs,
   __shared__ uint32_t s_scratch[kBtcWarps + 1];
   __shared__ unsigned long long s_chunk;
   __shared__ int s_fail;
+  // packed payload of one tile, staged by a TMA bulk copy (cp.async.bulk -> mbarrier): the unpack
+  // loads then hit shared memory instead of stalling on global memory (long-scoreboard was the top stall)
+  __shared__ __align__(128) uint8_t s_stage[kBtcStage];
+  __shared__ __align__(8) unsigned long long s_mbar;
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(s_stage);
+  uint32_t parity = 0;
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  __syncthreads();
   size_t static_next = blockIdx.x;
   while (true) {
     if (threadIdx.x == 0) {
@@ -234,11 +244,26 @@ bitcomp_decompress_kernel(const void* const* __restrict__ comp_ptrs,
         __syncthreads();
         if (!s_fail) {
           const uint32_t nb = min(kBtcTile, h.nblocks - tile);
+          // stage [base_off, base_off + total) (16-byte aligned span around it) if it fits
+          const uint8_t* tile_src = in + base_off;
+          const uint32_t delta = (uint32_t)((uintptr_t)tile_src & 15u);
+          const uint32_t span = (delta + total + 15u) & ~15u;
+          const bool staged = total != 0u && span <= kBtcStage;
+          if (staged) {
+            if (threadIdx.x == 0) {
+              fence_proxy_async_smem();
+              mbar_expect_tx(mbar, span);
+              tma_bulk_g2s(stage_s, tile_src - delta, span, mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+          }
+          const uint8_t* pay_base = staged ? (const uint8_t*)s_stage + delta - base_off : in;
           for (uint32_t b = w; b < nb; b += kBtcWarps) {
             const uint32_t blk = tile + b;
             const uint32_t e0 = blk * kBtcBlock;
             const uint32_t nv = min(kBtcBlock, n_elems - e0);
-            const uint8_t* payload = in + s_off[b];
+            const uint8_t* payload = pay_base + s_off[b];
             const uint32_t d = s_desc[b];
             switch (ts) {
               case 1: btc_decode_block<1>(h.algo, d, payload, (uint8_t*)out + e0, nv, lane); break;

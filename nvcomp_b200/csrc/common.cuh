@@ -215,6 +215,39 @@ __device__ __forceinline__ void warp_match_copy(uint8_t* dst, uint32_t off, uint
   }
 }
 
+// ---------------------------------------------------------------------------
+// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: one thread stages a
+// 16-byte aligned span of global memory into shared memory asynchronously; consumers wait on
+// the mbarrier's phase.  Addresses are 32-bit shared-window addresses.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" :: "r"(mbar), "r"(parity) : "memory");
+}
+// order this thread's earlier generic-proxy accesses to shared memory before later async-proxy writes
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// smem_dst, gmem_src and bytes must be multiples of 16
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
+}
+
 // Host-side launch helper: number of CTAs for a persistent kernel.
 inline int persistent_grid(int ctas_per_sm, size_t work_items, int work_per_cta) {
   size_t need = (work_items + (size_t)work_per_cta - 1) / (size_t)work_per_cta;
