@@ -323,7 +323,7 @@ nvcompStatus_t nvcompBatchedLZ4CompressAsync(
         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int grid = persistent_grid(3, batch, kCompWarpsPerCta);
+  const int grid = persistent_grid(6, batch, kCompWarpsPerCta);
   lz4_compress_kernel<<<grid, kCompWarpsPerCta * 32, smem, stream>>>(
       in_ptrs, in_bytes, batch, out_ptrs, out_bytes, step, ticket);
   B200_CUDA_TRY(cudaGetLastError());

@@ -3,7 +3,7 @@
 //
 // One warp owns one chunk.  Each round the 32 lanes hash 32 consecutive
 // candidate positions, probe a shared-memory hash table (uint16 positions,
-// 8192 entries = 16 KB per warp), vote with a ballot for the first verified
+// 4096 entries = 8 KB per warp), vote with a ballot for the first verified
 // match, extend it cooperatively (32 bytes per compare round) and hand the
 // (literal run, offset, length) sequence to the format-specific Emitter.
 //
@@ -16,9 +16,9 @@
 
 namespace b200 {
 
-constexpr int kHashLog = 13;
+constexpr int kHashLog = 12;             // 4096 entries (LZ4's default table size for 64 KB blocks)
 constexpr int kHashEntries = 1 << kHashLog;           // uint16 entries
-constexpr int kHashBytesPerWarp = kHashEntries * 2;   // 16 KB
+constexpr int kHashBytesPerWarp = kHashEntries * 2;   // 8 KB
 
 __device__ __forceinline__ uint32_t hash4(uint32_t v) {
   return (v * 2654435761u) >> (32 - kHashLog);

@@ -416,7 +416,7 @@ nvcompStatus_t nvcompBatchedSnappyCompressAsync(
         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int grid = persistent_grid(3, batch, kSnappyCompWarps);
+  const int grid = persistent_grid(6, batch, kSnappyCompWarps);
   snappy_compress_kernel<<<grid, kSnappyCompWarps * 32, smem, stream>>>(
       in_ptrs, in_bytes, batch, out_ptrs, out_bytes, ticket);
   B200_CUDA_TRY(cudaGetLastError());
