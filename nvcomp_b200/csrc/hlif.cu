@@ -540,3 +540,12 @@ std::shared_ptr<nvcompManagerBase> create_manager(const uint8_t* comp_buffer, cu
 B200_UNSUPPORTED_LLIF(Gdeflate)
 B200_UNSUPPORTED_LLIF(Deflate)
 B200_UNSUPPORTED_LLIF(Zstd)
+
+#include "nvcomp/gzip.h"
+extern "C" {
+nvcompStatus_t nvcompBatchedGzipDecompressGetTempSize(size_t, size_t, size_t*) { return nvcompErrorNotSupported; }
+nvcompStatus_t nvcompBatchedGzipGetDecompressSizeAsync(const void* const*, const size_t*, size_t*, size_t, cudaStream_t) {
+  return nvcompErrorNotSupported; }
+nvcompStatus_t nvcompBatchedGzipDecompressAsync(const void* const*, const size_t*, const size_t*, size_t*, size_t,
+    void* const, size_t, void* const*, nvcompStatus_t*, cudaStream_t) { return nvcompErrorNotSupported; }
+}

@@ -74,3 +74,16 @@ def test_unsupported_formats_report_not_supported(data_files):
         pytest.skip("not built")
     r = subprocess.run([exe, "-f", data_files["bytes"]], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0     # out-of-scope format: the harness' status assert fires, nothing crashes
+
+
+def test_cmake_built_reference_binary_runs():
+    """A binary produced by the reference's OWN CMake build against cmake/nvcomp-config.cmake
+    (build/ref_cmake, built where /root/reference exists; PTX-JIT from compute_90 on B200)."""
+    exe = os.path.join(ROOT, "build", "ref_cmake", "bin", "low_level_quickstart_example")
+    if not os.path.exists(exe):
+        pytest.skip("build/ref_cmake not present")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    exe = os.path.join(ROOT, "build", "ref_cmake", "bin", "benchmark_snappy_synth")
+    r = subprocess.run([exe, "-b", "200", "-w", "1", "-i", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "decompression throughput (GB/s)" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
