@@ -55,6 +55,13 @@ def test_snappy_synth():
     assert "decompression throughput (GB/s)" in out and "Mismatch" not in out and "failed" not in out
 
 
+def test_lz4_synth_hlif():
+    """benchmark_lz4_synth: LZ4Manager round trips of all-zero and all-random buffers, 64 KB ... 512 MB
+    (reference benchmarks/benchmark_lz4_synth.cpp:64-72; BASELINE configs[0] names this path)."""
+    out = _run("benchmark_lz4_synth", timeout=900)
+    assert out.count("decompression throughput (GB/s)") == 28
+
+
 def test_quickstarts():
     _run("low_level_quickstart_example")
     _run("high_level_quickstart_example")

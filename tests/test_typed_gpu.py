@@ -143,3 +143,26 @@ def test_typed_batch_roundtrip_property(kind, dataset):
     assert (status == 0).all().item()
     assert (actual == 65536).all().item()
     assert torch.equal(out.slab[: n * 65536], slab)
+
+
+@pytest.mark.parametrize("kind", ["LZ4", "Snappy", "Cascaded", "Bitcomp", "ANS"])
+def test_maximum_chunk_size(kind, oracle):
+    """Chunks up to nvcomp<Fmt>CompressionMaxAllowedChunkSize (16 MB): round trip bit-exact, GPU stream decodes
+    with the CPU oracle; one byte more is rejected with nvcompErrorChunkSizeTooLarge."""
+    from gpu_util import gpu_compress, gpu_decompress
+    from nvcomp_b200 import datagen
+    from nvcomp_b200._lib import BitcompOpts, CascadedOpts
+    from nvcomp_b200.batched import Codec, NvcompError
+    opts = {"Cascaded": CascadedOpts(4096, 4, 1, 1, 1), "Bitcomp": BitcompOpts(0, 5)}.get(kind)
+    codec = Codec(kind, opts=opts)
+    big = np.concatenate([datagen.runlength_i32(64, seed=3).reshape(-1), datagen.tabular_f32(128, seed=4).reshape(-1),
+                          datagen.lowentropy_bytes(64, seed=5).reshape(-1)])          # 16 MB
+    assert big.size == 1 << 24
+    raws = [big.tobytes(), big[: (1 << 20) + 8].tobytes()]
+    comps, _ = gpu_compress(codec, raws)
+    okind = {"LZ4": "lz4", "Snappy": "snappy", "Cascaded": "cascaded", "Bitcomp": "bitcomp", "ANS": "ans"}[kind]
+    assert oracle.decompress(okind, comps[1], len(raws[1])) == raws[1]
+    outs, actual, status, _ = gpu_decompress(codec, comps, [len(r) for r in raws])
+    assert (status == 0).all() and outs == raws
+    with pytest.raises(NvcompError):
+        codec.compress_get_max_output_chunk_size((1 << 24) + 1)
