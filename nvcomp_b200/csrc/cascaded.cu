@@ -32,7 +32,6 @@ namespace b200 {
 constexpr uint32_t kCascMagic = 0x31435343u;  // "CSC1"
 constexpr int kCascWarps = 16;       // decode CTA: up to 16 warps, one partition each
 constexpr int kCascCompWarps = 4;    // compress CTA
-constexpr uint32_t kCascFastPart = 4096;      // partitions up to this size: one warp each
 constexpr uint32_t kCascMaxPart = 16384;
 // per-warp shared memory of the decoder: one value buffer (P bytes; two when more than one layer pair
 // is configured) + a run-index u16 array (2 * P/TS bytes).  The CTA owns 96 KB and activates as many

@@ -5,10 +5,10 @@
 // liblz4 1.9.4 in both directions (reference examples/lz4_cpu_compression.cu,
 // examples/lz4_cpu_decompression.cu).
 //
-// Decode: one warp owns one chunk; chunks are handed out by a persistent
-// ticket scheduler.  Token fields are parsed warp-uniformly; literal runs and
-// match runs move as 16-byte vectors (common.cuh: warp_copy / warp_match_copy).
-#include <cstdlib>
+// Decode: one warp owns one chunk; chunks are handed out by a persistent two-pass ticket
+// scheduler (dense chunks first).  Dense short-token chunks use the lane-parallel decoder of
+// lz_decode.cuh; chunks that compressed >= 4x use the direct token loop below (warp-uniform
+// parse, 16-byte vector copies: common.cuh warp_copy / warp_match_copy).
 #include "common.cuh"
 #include "lz77_compress.cuh"
 #include "lz_decode.cuh"
@@ -163,9 +163,10 @@ __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t 
 }
 
 constexpr int kLzDecWarps = 4;
+// 10 CTAs x 4 warps per SM (48 registers): measured best of 8 / 10 / 12 (profiles/README.md)
+constexpr int kLzDecCtasPerSm = 10;
 
-template <int kMinCtas>
-__global__ void __launch_bounds__(kLzDecWarps * 32, kMinCtas)
+__global__ void __launch_bounds__(kLzDecWarps * 32, kLzDecCtasPerSm)
 lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
                          const size_t* __restrict__ comp_bytes,
                          const size_t* __restrict__ out_caps,
@@ -367,28 +368,9 @@ nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
     ticket = (unsigned long long*)temp;
     B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned long long), stream));
   }
-  static const bool use_v1 = getenv("NVCOMP_B200_LZ_V1") != nullptr;   // developer A/B switch
-  if (use_v1) {
-    const int grid = persistent_grid(10, batch, 4);
-    lz4_decompress_kernel<true><<<grid, 128, 0, stream>>>(
-        comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-  } else {
-    static const char* occ_env = getenv("NVCOMP_B200_LZ_OCC");   // developer A/B switch: CTAs per SM
-    const int occ = occ_env ? atoi(occ_env) : 10;   // measured best (profiles/): 40 warps/SM, 48 registers
-    if (occ >= 12) {
-      const int grid = persistent_grid(12, batch, kLzDecWarps);
-      lz4_decompress_v2_kernel<12><<<grid, kLzDecWarps * 32, 0, stream>>>(
-          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-    } else if (occ >= 10) {
-      const int grid = persistent_grid(10, batch, kLzDecWarps);
-      lz4_decompress_v2_kernel<10><<<grid, kLzDecWarps * 32, 0, stream>>>(
-          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-    } else {
-      const int grid = persistent_grid(8, batch, kLzDecWarps);
-      lz4_decompress_v2_kernel<8><<<grid, kLzDecWarps * 32, 0, stream>>>(
-          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-    }
-  }
+  const int grid = persistent_grid(kLzDecCtasPerSm, batch, kLzDecWarps);
+  lz4_decompress_v2_kernel<<<grid, kLzDecWarps * 32, 0, stream>>>(
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
   B200_CUDA_TRY(cudaGetLastError());
   return nvcompSuccess;
 }

@@ -1,25 +1,25 @@
 // lz_decode.cuh -- lane-parallel LZ77 (LZ4 / Snappy) chunk decoder for B200.
 //
-// One warp owns one chunk.  The decoder is organised around the observation that on
-// tabular data a 64 KB chunk holds 10-15 thousand *short* tokens (4-8 output bytes
-// each), so throughput is bounded by warp-instructions per token, not by bytes:
+// One warp owns one chunk.  On tabular data a 64 KB chunk holds 10-15 thousand *short* tokens
+// (4-8 output bytes each), so throughput is bounded by warp-instructions per token, not bytes:
 //
-//  * FAST PATH (short tokens).  The 32 lanes look at 32 consecutive input bytes.
-//    Every lane parses the byte under it as if it were a token start (speculative
-//    parse), the true token chain is recovered with 4 rounds of pointer doubling
-//    (__reduce_or_sync + __shfl_sync), a warp scan of the token output lengths gives
-//    every token its output position, literals are scattered in one pass straight from
-//    registers, and the matches are copied one token per lane in dependency rounds
-//    (a match is ready once everything below its source end has been written).
-//    ~10 tokens retire per iteration instead of one.
-//  * The most recent 4 KB of output live in a per-warp shared-memory ring, so match
-//    sources are read at shared-memory latency; completed 512-byte blocks are flushed
-//    to HBM with 16-byte aligned vector stores (full-line writes).  Matches that reach
-//    further back than the ring read the already flushed bytes from global memory.
-//  * SLOW PATH (long tokens: length-extension bytes, >18-byte matches, ...).  The ring
-//    is flushed and the token is executed by the whole warp directly on global memory
-//    with 16-byte vector copies (common.cuh warp_copy / warp_match_copy), then the ring
-//    restarts empty.  Runs of long tokens stay in this mode.
+//  * FAST PATH (short tokens, lz_fast_iter).  The 32 lanes look at 32 consecutive input bytes.
+//    Every lane parses the byte under it as if it were a token start (speculative parse), the true
+//    token chain is recovered with 4 rounds of pointer doubling (__reduce_or_sync + __shfl_sync), a
+//    warp scan of the token output lengths gives every token its output position, literals are
+//    scattered in one pass straight from registers, matches whose sources are already final are
+//    copied one per lane with branch-free tiers, the few that depend on output of the same window
+//    are retired in order (whole warp, one byte per lane).  ~14 tokens retire per iteration.
+//  * The most recent 4 KB of output live in a per-warp shared-memory ring (explicit 32-bit shared
+//    addressing), so match sources are read at shared-memory latency; completed 512-byte blocks are
+//    flushed to HBM with 16-byte aligned vector stores (full-line writes, DRAM traffic == algorithmic
+//    bytes).  Matches that reach further back than the ring read the flushed bytes from global memory.
+//  * SERIAL PATH (P::serial_token + lz_emit_*): tokens with length-extension bytes / long lengths are
+//    parsed once by the whole warp; up to 192 bytes they are executed inside the ring, longer runs go
+//    straight to global memory as 16-byte vectors (periodic runs are built in registers, no
+//    store->load round trip) and the ring restarts empty behind them.
+//  * Chunks that compressed >= 4x never enter this machinery: the callers (lz4.cu / snappy.cu) decode
+//    them with the direct global-memory token loop, and hand dense chunks out first (two-pass ticket).
 //
 // Format specifics (token grammar, stream end, size limits) come from a Parse policy.
 #pragma once
@@ -31,6 +31,7 @@ namespace b200 {
 constexpr uint32_t kRingBytes = 4096;
 constexpr uint32_t kRingMask = kRingBytes - 1;
 constexpr uint32_t kFlushBlock = 512;
+constexpr int kParRounds = 3;          // parallel match rounds per window before in-order retirement
 // A match source is served from the ring only if it is younger than this many bytes
 // (ring size minus the largest output one fast iteration can append, minus alignment slack).
 constexpr uint32_t kRingReach = kRingBytes - 1024 - 16;
@@ -166,20 +167,6 @@ struct SnappyPolicy {
   __device__ static __forceinline__ bool is_stop(uint32_t b0) { return parse(b0).stop; }
 };
 
-// Copy one short match (one lane = one token) inside the ring / from global memory.
-__device__ __forceinline__ void lane_match_copy(const LzState& s, uint32_t ring_from, uint32_t dst,
-                                                uint32_t off, uint32_t M) {
-  const uint32_t src = dst - off;
-  uint32_t r = 0;                            // source index modulo off (overlapping matches replicate)
-  for (uint32_t i = 0; i < M; ++i) {
-    const uint32_t sp = src + r;
-    const uint32_t b = (sp >= ring_from) ? ring_ld(s, sp) : (uint32_t)s.out[sp];
-    ring_st(s, dst + i, b);
-    ++r;
-    if (r == off) r = 0;
-  }
-}
-
 // One fast-path iteration.  Returns number of tokens retired (0: the token at s.ip needs
 // the slow path), or -1 on a malformed stream.
 template <class P>
@@ -266,12 +253,17 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
     const bool simple = has_match && off >= t.M && didx <= kRingBytes - 20u && (in_ring || far);
     const uint32_t dp = rbase + didx, sp = rbase + sidx;
     const uint8_t* const gp = outa + src0;
+    // up to kParRounds parallel rounds: each takes every pending match whose source ends at or below
+    // the output position of the first pending match (everything below it is final)
+    for (int rnd = 0; rnd < kParRounds && pending; ++rnd) {
     __syncwarp();
     const int first0 = __ffs(pending) - 1;
-    const uint32_t w = __shfl_sync(kFull, o_mat, first0);    // everything below w is final
-    const bool ready = has_match && (src_end <= w);
+    const uint32_t w = __shfl_sync(kFull, o_mat, first0);
+    const bool ready = ((pending >> lane) & 1u) && (src_end <= w);
     const bool fast = ready && simple;
     const bool fast_r = fast && !far, fast_g = fast && far;
+    const unsigned fmask = __ballot_sync(kFull, fast);
+    if (fmask == 0u) break;                                  // first pending match needs the generic path
 #define B200_TIER4(LD, SRC, A, B, C, D)                                                        \
     {                                                                                          \
       const uint32_t x0 = LD<A>(SRC), x1 = LD<B>(SRC), x2 = LD<C>(SRC), x3 = LD<D>(SRC);       \
@@ -305,9 +297,10 @@ __device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
         }
       }
     }
+    pending &= ~fmask;
+    }
 #undef B200_TIER4
 #undef B200_TAIL10
-    pending &= ~__ballot_sync(kFull, fast);
     // in-order retirement of everything else
     while (pending) {
       __syncwarp();

@@ -5,7 +5,6 @@
 // benchmarks/benchmark_snappy_chunked.cu:51-55).  The decoder accepts every legal
 // Snappy stream: literal tags with 0..4 length bytes and copy-1 / copy-2 / copy-4
 // elements (reference CHANGELOG.md:182-184).
-#include <cstdlib>
 #include "common.cuh"
 #include "lz77_compress.cuh"
 #include "lz_decode.cuh"
@@ -101,34 +100,6 @@ __device__ __forceinline__ bool snappy_decode_chunk(const uint8_t* __restrict__ 
   return true;
 }
 
-__global__ void __launch_bounds__(128)
-snappy_decompress_kernel(const void* const* __restrict__ comp_ptrs,
-                         const size_t* __restrict__ comp_bytes,
-                         const size_t* __restrict__ out_caps,
-                         size_t* actual_bytes, size_t batch,
-                         void* const* __restrict__ out_ptrs,
-                         nvcompStatus_t* statuses,
-                         unsigned long long* ticket) {
-  const int lane = lane_id();
-  const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
-  WarpTicket sched(ticket, warp_global, warps_total);
-  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
-    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
-    const size_t in_n64 = comp_bytes[c];
-    uint8_t* out = (uint8_t*)out_ptrs[c];
-    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
-    const uint64_t cap = (uint64_t)out_caps[c];
-    uint32_t produced = 0;
-    bool ok = in_n64 <= 0xffffffffull;
-    if (ok) ok = snappy_decode_chunk(in, (uint32_t)in_n64, out, cap, &produced, lane);
-    if (lane == 0) {
-      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
-      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
-    }
-  }
-}
-
 
 // ---------------------------------------------------------------------------
 // v2 decode (lz_decode.cuh): lane-parallel short-element path + this slow path
@@ -221,9 +192,10 @@ __device__ __forceinline__ bool snappy_decode_chunk_v2(const uint8_t* in, uint32
 }
 
 constexpr int kLzDecWarps = 4;
+// 10 CTAs x 4 warps per SM (48 registers): measured best of 8 / 10 / 12 (profiles/README.md)
+constexpr int kLzDecCtasPerSm = 10;
 
-template <int kMinCtas>
-__global__ void __launch_bounds__(kLzDecWarps * 32, kMinCtas)
+__global__ void __launch_bounds__(kLzDecWarps * 32, kLzDecCtasPerSm)
 snappy_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
                             const size_t* __restrict__ comp_bytes,
                             const size_t* __restrict__ out_caps,
@@ -458,28 +430,9 @@ nvcompStatus_t nvcompBatchedSnappyDecompressAsync(
     ticket = (unsigned long long*)temp;
     B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned long long), stream));
   }
-  static const bool use_v1 = getenv("NVCOMP_B200_LZ_V1") != nullptr;   // developer A/B switch
-  if (use_v1) {
-    const int grid = persistent_grid(10, batch, 4);
-    snappy_decompress_kernel<<<grid, 128, 0, stream>>>(
-        comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-  } else {
-    static const char* occ_env = getenv("NVCOMP_B200_LZ_OCC");   // developer A/B switch: CTAs per SM
-    const int occ = occ_env ? atoi(occ_env) : 10;   // measured best (profiles/): 40 warps/SM, 48 registers
-    if (occ >= 12) {
-      const int grid = persistent_grid(12, batch, kLzDecWarps);
-      snappy_decompress_v2_kernel<12><<<grid, kLzDecWarps * 32, 0, stream>>>(
-          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-    } else if (occ >= 10) {
-      const int grid = persistent_grid(10, batch, kLzDecWarps);
-      snappy_decompress_v2_kernel<10><<<grid, kLzDecWarps * 32, 0, stream>>>(
-          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-    } else {
-      const int grid = persistent_grid(8, batch, kLzDecWarps);
-      snappy_decompress_v2_kernel<8><<<grid, kLzDecWarps * 32, 0, stream>>>(
-          comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
-    }
-  }
+  const int grid = persistent_grid(kLzDecCtasPerSm, batch, kLzDecWarps);
+  snappy_decompress_v2_kernel<<<grid, kLzDecWarps * 32, 0, stream>>>(
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
   B200_CUDA_TRY(cudaGetLastError());
   return nvcompSuccess;
 }
