@@ -7,7 +7,7 @@
 //   decompress: scan of the size table -> pointer setup -> nvcompBatched<Fmt>DecompressAsync ->
 //               status reduction into pinned host memory (DecompressionConfig::get_status()).
 // Container (8-byte aligned):
-//   HlifHeader (64 B) | u64 chunk_bytes[num_chunks] | chunks (each 8-byte aligned)
+//   HlifHeader (72 B) | u64 chunk_bytes[num_chunks] | chunks (each 8-byte aligned)
 // Checksums (optional, ChecksumPolicy): a 32-bit position-mixed sum of the uncompressed buffer and
 // of the compressed payload -- like the reference's HLIF checksum it is *not* a standard CRC32
 // (doc/highlevel_cpp_quickstart.md:59).
@@ -38,7 +38,7 @@ struct HlifHeader {
   uint32_t checksum_uncomp;
   uint32_t checksum_comp;
 };
-static_assert(sizeof(HlifHeader) == 72 || sizeof(HlifHeader) == 64, "header layout");
+static_assert(sizeof(HlifHeader) == 72, "header layout");
 constexpr size_t kHeaderBytes = 72;
 
 struct StatusHolder {
@@ -215,25 +215,6 @@ __global__ void hlif_store_checksums(uint8_t* comp_buffer, const uint32_t* sums)
   HlifHeader* h = (HlifHeader*)comp_buffer;
   h->checksum_uncomp = sums[0];
   h->checksum_comp = sums[1];
-}
-
-// fold per-chunk statuses (+ optional checksum comparison) into one pinned host status
-__global__ void hlif_reduce_status(const nvcompStatus_t* statuses, size_t num_chunks, const uint8_t* comp_buffer,
-                                   const uint32_t* sums, int verify, nvcompStatus_t* host_status) {
-  __shared__ int s_bad;
-  if (threadIdx.x == 0) s_bad = 0;
-  __syncthreads();
-  for (size_t i = threadIdx.x; i < num_chunks; i += blockDim.x)
-    if (statuses[i] != nvcompSuccess) s_bad = 1;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    nvcompStatus_t st = s_bad ? nvcompErrorCannotDecompress : nvcompSuccess;
-    if (st == nvcompSuccess && verify) {
-      const HlifHeader* h = (const HlifHeader*)comp_buffer;
-      if (h->checksum_uncomp != sums[0] || h->checksum_comp != sums[1]) st = nvcompErrorBadChecksum;
-    }
-    *host_status = st;
-  }
 }
 
 __global__ void hlif_set_status(nvcompStatus_t* host_status, nvcompStatus_t v) { *host_status = v; }
