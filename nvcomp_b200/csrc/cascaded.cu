@@ -104,6 +104,17 @@ __device__ __forceinline__ uint64_t unpack_at(const uint64_t* __restrict__ words
   return v + minv;
 }
 
+// bits <= 32: the stream is read as 32-bit words, one funnel shift per value (bits is uniform over a
+// stream, so callers branch once per stream, not per value)
+__device__ __forceinline__ uint64_t unpack32_at(const uint32_t* __restrict__ w32, uint32_t k,
+                                                uint32_t bits, uint32_t mask, uint64_t minv) {
+  const uint32_t bitpos = k * bits;                  // < 2^19: count <= 16384, bits <= 32
+  const uint32_t w = bitpos >> 5, s = bitpos & 31u;
+  const uint32_t lo = w32[w];
+  const uint32_t hi = (s + bits > 32u) ? w32[w + 1] : 0u;
+  return (uint64_t)(__funnelshift_r(lo, hi, s) & mask) + minv;
+}
+
 __host__ __device__ inline uint32_t stream_bytes(uint32_t count, uint32_t bits) {
   return 16u + 8u * (uint32_t)(((uint64_t)count * bits + 63) / 64);
 }
@@ -160,7 +171,13 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
 
   // unpack the final value stream into A
   uint32_t count = vh.count;
-  for (uint32_t k = lane; k < count; k += kWarp) bufA[k] = (T)unpack_at(vwords, k, vh.bits, vh.minv);
+  if (vh.bits != 0u && vh.bits <= 32u) {
+    const uint32_t* w32 = (const uint32_t*)vwords;
+    const uint32_t mask = vh.bits == 32u ? 0xffffffffu : ((1u << vh.bits) - 1u);
+    for (uint32_t k = lane; k < count; k += kWarp) bufA[k] = (T)unpack32_at(w32, k, vh.bits, mask, vh.minv);
+  } else {
+    for (uint32_t k = lane; k < count; k += kWarp) bufA[k] = (T)unpack_at(vwords, k, vh.bits, vh.minv);
+  }
   __syncwarp();
   T* cur = bufA;
   const int L = R > D ? R : D;
@@ -204,9 +221,15 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
       }
       __syncwarp();
       uint32_t carry = 0;
+      const bool narrow = rh.bits != 0u && rh.bits <= 32u;
+      const uint32_t* rw32 = (const uint32_t*)rwords;
+      const uint32_t rmask = rh.bits >= 32u ? 0xffffffffu : ((1u << rh.bits) - 1u);
       for (uint32_t base = 0; base < count; base += kWarp) {
         const uint32_t k = base + lane;
-        const uint32_t len = (k < count) ? (uint32_t)unpack_at(rwords, k, rh.bits, rh.minv) : 0u;
+        uint32_t len = 0u;
+        if (k < count)
+          len = narrow ? (uint32_t)unpack32_at(rw32, k, rh.bits, rmask, rh.minv)
+                       : (uint32_t)unpack_at(rwords, k, rh.bits, rh.minv);
         const uint32_t incl = warp_incl_scan_u32(len, lane) + carry;
         carry = __shfl_sync(kFull, incl, 31);
         if (carry > cap) return false;
