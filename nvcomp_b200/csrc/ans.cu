@@ -50,6 +50,32 @@ __device__ __forceinline__ bool ans_read_header(const uint8_t* in, size_t in_byt
   return true;
 }
 
+__device__ __forceinline__ uint32_t ans_lds(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
+constexpr uint32_t kAnsRingBlocks = 8;                      // 64-word (128-byte) blocks per warp ring
+constexpr uint32_t kAnsRingWords = kAnsRingBlocks * 64;     // 512 words = 1 KB per warp
+
+__device__ __forceinline__ uint32_t ans_lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ans_mad(uint32_t a, uint32_t b, uint32_t c) {   // one IMAD
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ void ans_cp_async4(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void ans_cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kAnsThreads)
 ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
                       const size_t* __restrict__ comp_bytes,
@@ -60,10 +86,13 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
                       unsigned long long* ticket) {
   __shared__ uint32_t s_lut[kAnsM];
   __shared__ uint32_t s_cum[257];
+  __shared__ __align__(1024) uint16_t s_wring[kAnsWarps][kAnsRingWords];   // 1 KB per warp, 1 KB aligned
   __shared__ unsigned long long s_chunk;
   __shared__ int s_fail;
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
+  const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_lut);
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&s_wring[0][0]);
   size_t static_next = blockIdx.x;
   while (true) {
     if (threadIdx.x == 0) {
@@ -83,8 +112,10 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
     bool ok = ans_read_header(in, in_bytes, h);
     if (ok && h.n > out_caps[c]) ok = false;
     if (ok && h.mode == 1) {
-      // stored: block-wide copy
-      for (uint32_t i = threadIdx.x; i < h.n; i += kAnsThreads) out[i] = in[16 + i];
+      // stored: every warp copies one contiguous slice as 16-byte vectors
+      const uint32_t slice = (((h.n + kAnsWarps - 1) / kAnsWarps) + 15u) & ~15u;
+      const uint32_t b0 = min((uint32_t)w * slice, h.n), b1 = min(b0 + slice, h.n);
+      if (b1 > b0) warp_copy<true>(out + b0, in + 16 + b0, b1 - b0, lane);
     } else if (ok && h.mode == 2) {
       const uint8_t sym = in[16];
       for (uint32_t i = threadIdx.x; i < h.n; i += kAnsThreads) out[i] = sym;
@@ -108,14 +139,20 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
       }
       __syncthreads();
       if (!s_fail) {
-        // fill the LUT: warp w owns symbols w, w+4, ...; its lanes stride over the symbol's slots
-        // (no dependent search chains: two table reads per symbol, then independent stores)
-        for (uint32_t sym = w; sym < 256; sym += kAnsWarps) {
-          const uint32_t c0 = s_cum[sym], c1 = s_cum[sym + 1];
-          const uint32_t f = c1 - c0;
-          if (f > 4095u) s_fail = 1;
-          const uint32_t base = sym | ((f & 0xfffu) << 8);
-          for (uint32_t slot = c0 + lane; slot < c1; slot += kWarp) s_lut[slot] = base | ((slot - c0) << 20);
+        // fill the LUT: warp w owns symbols 64w .. 64w+63; a ballot finds the symbols that occur (a
+        // low-entropy chunk uses a few dozen of the 256), then the lanes stride over each one's slots
+        for (uint32_t half = 0; half < 2; ++half) {
+          const uint32_t my_sym = 64u * (uint32_t)w + 32u * half + (uint32_t)lane;
+          const uint32_t my_c0 = s_cum[my_sym], my_f = s_cum[my_sym + 1] - my_c0;
+          if (my_f > 4095u) s_fail = 1;
+          unsigned present = __ballot_sync(kFull, my_f != 0u);
+          while (present) {
+            const int k = __ffs(present) - 1;
+            present &= present - 1u;
+            const uint32_t c0 = __shfl_sync(kFull, my_c0, k), f = __shfl_sync(kFull, my_f, k);
+            const uint32_t base = (64u * (uint32_t)w + 32u * half + (uint32_t)k) | ((f & 0xfffu) << 8);
+            for (uint32_t i = lane; i < f; i += kWarp) s_lut[c0 + i] = base | (i << 20);
+          }
         }
       }
       __syncthreads();
@@ -128,41 +165,87 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
             const uint32_t begin = sg * kAnsSeg;
             const uint32_t ns = min(kAnsSeg, h.n - begin);
             uint32_t x = ((const uint32_t*)(in + o0))[lane];
-            const uint16_t* __restrict__ words = (const uint16_t*)(in + o0 + 128);
             const uint32_t nwords = (o1 - o0 - 128u) >> 1;
             uint32_t wpos = 0;
             uint8_t* o = out + begin + lane;
             const unsigned lt = (1u << lane) - 1u;
-            // full rounds: every lane decodes one symbol; straight-line, the only predicated
-            // instruction is the renormalisation word load
+            // The renormalisation words stream through a per-warp shared-memory ring (8 blocks of 64
+            // words, filled by 4-byte cp.async several blocks ahead of the read position), so the
+            // per-round dependent chain holds an LDS instead of a global load that misses L1 every
+            // fourth round.  A malformed stream that asks for more words than it has reads stale ring
+            // contents (never out of bounds) and fails the integrity check below.
+            const uint32_t wring = ring0 + (uint32_t)w * (kAnsRingWords * 2u);
+            const uint8_t* wbytes = in + o0 + 128;
+            const uint32_t wbytes_n = nwords * 2u;
+            uint32_t issued = 0;                      // 64-word blocks requested so far
+            bool in_flight = false;                   // cp.async issued and not yet waited for
+            auto ring_top = [&]() {
+              // before a group of <= 8 rounds (<= 256 words): blocks kb .. kb+4 must be resident.
+              // Common case: nothing to wait for, nothing to issue (a block lasts ~16 rounds).
+              const uint32_t kb = wpos >> 6;
+              if (in_flight) { ans_cp_async_wait_all(); __syncwarp(); in_flight = false; }
+              if (issued < kb + kAnsRingBlocks && issued * 128u < wbytes_n) {
+                bool urgent = false;
+                do {
+                  const uint32_t boff = issued * 128u + (uint32_t)lane * 4u;
+                  if (boff < wbytes_n) ans_cp_async4(wring + (boff & (kAnsRingWords * 2u - 1u)), wbytes + boff);
+                  urgent |= issued < kb + 5u;
+                  ++issued;
+                } while (issued < kb + kAnsRingBlocks);
+                in_flight = true;
+                if (urgent) { ans_cp_async_wait_all(); __syncwarp(); in_flight = false; }
+              }
+            };
+            // full rounds: every lane decodes one symbol; straight-line, nothing predicated
             const uint32_t full = ns >> 5;
-            for (uint32_t r = 0; r < full; ++r) {
-              const uint32_t e = s_lut[x & (kAnsM - 1)];
-              o[r << 5] = (uint8_t)e;
-              x = ((e >> 8) & 0xfffu) * (x >> kAnsLog) + (e >> 20);
-              const bool need = x < kAnsLow;
-              const unsigned m = __ballot_sync(kFull, need);
-              const uint32_t idx = wpos + __popc(m & lt);
-              uint32_t wd = 0;
-              if (need && idx < nwords) wd = words[idx];
-              x = need ? ((x << 16) | wd) : x;
-              wpos += __popc(m);
+#define B200_ANS_ROUND(OFF)                                                              \
+  {                                                                                      \
+    const uint32_t e = ans_lds(ans_mad(x & (kAnsM - 1), 4u, lut));                       \
+    o[OFF] = (uint8_t)e;                                                                 \
+    x = ((e >> 8) & 0xfffu) * (x >> kAnsLog) + (e >> 20);                                \
+    const bool need = x < kAnsLow;                                                       \
+    const unsigned m = __ballot_sync(kFull, need);                                       \
+    /* byte offset of this lane's word in the ring; the ring is 1 KB aligned: (off & mask) | base */ \
+    const uint32_t boff = ans_mad(__popc(m & lt), 2u, wpos2);                            \
+    const uint32_t wd = ans_lds_u16((boff & (kAnsRingWords * 2u - 2u)) | wring);         \
+    x = need ? __byte_perm(wd, x, 0x5410) : x;                                           \
+    wpos2 = ans_mad(__popc(m), 2u, wpos2);                                               \
+  }
+            uint32_t r = 0;
+            uint32_t wpos2 = 0;                       // 2 * wpos (byte position in the word stream)
+            for (; r + 8 <= full; r += 8) {
+              wpos = wpos2 >> 1;
+              ring_top();
+              B200_ANS_ROUND(0) B200_ANS_ROUND(32) B200_ANS_ROUND(64) B200_ANS_ROUND(96)
+              B200_ANS_ROUND(128) B200_ANS_ROUND(160) B200_ANS_ROUND(192) B200_ANS_ROUND(224)
+              o += 256;
             }
+            wpos = wpos2 >> 1;
+            ring_top();                                // covers the < 8 remaining rounds + the tail round
+            for (; r < full; ++r) {
+              B200_ANS_ROUND(0)
+              o += 32;
+            }
+            wpos = wpos2 >> 1;
+#undef B200_ANS_ROUND
             // tail round (ns % 32 symbols)
             if (ns & 31u) {
               const bool active = (uint32_t)lane < (ns & 31u);
               bool need = false;
               if (active) {
                 const uint32_t e = s_lut[x & (kAnsM - 1)];
-                o[full << 5] = (uint8_t)e;
+                o[0] = (uint8_t)e;
                 x = ((e >> 8) & 0xfffu) * (x >> kAnsLog) + (e >> 20);
                 need = x < kAnsLow;
               }
               const unsigned m = __ballot_sync(kFull, need);
               const uint32_t idx = wpos + __popc(m & lt);
-              if (need) x = (x << 16) | ((idx < nwords) ? (uint32_t)words[idx] : 0u);
+              const uint32_t wd = ans_lds_u16(wring + ((idx & (kAnsRingWords - 1u)) << 1));
+              if (need) x = (x << 16) | wd;
               wpos += __popc(m);
             }
+            ans_cp_async_wait_all();                   // nothing in flight when the ring is reused
+            __syncwarp();
             // integrity: the stream must be consumed exactly and all states return to L
             const bool good = (nwords - wpos <= 1u) && (x == kAnsLow);   // <= 1: 4-byte pad word
             if (!__all_sync(kFull, good)) sok = false;
