@@ -76,6 +76,113 @@ __device__ __forceinline__ bool lz4_decode_chunk(const uint8_t* __restrict__ in,
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// Direct decode for chunks that compressed >= 4x (long matches, typed run-length data).  One coalesced
+// 32-byte load brings a whole sequence (token, short literals, offset, length-extension bytes) into a
+// register window; fields are extracted with warp OR-reductions, whose results are uniform registers,
+// so the token loop's control flow is provably uniform.  A match whose period (1, 2, 4 or 8 bytes) lies
+// inside the literals of its own sequence -- the shape of typed run-length data -- is expanded from the
+// window: the 8-byte period is rotated to the destination alignment and broadcast with 16-byte stores,
+// no load from the output buffer.  Everything else (other matches, sequences that do not fit the
+// window, the end of the block) takes the generic field-by-field path below.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lz_pick(uint32_t b, bool mine) {     // the byte of the lane(s) where `mine`
+  return __reduce_or_sync(kFull, mine ? b : 0u);
+}
+
+__device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restrict__ in, uint32_t in_n,
+                                                        uint8_t* out, uint64_t out_cap64,
+                                                        uint32_t* produced, int lane) {
+  if (in_n == 0) { *produced = 0; return true; }
+  const uint32_t cap = out_cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)out_cap64;
+  const uint32_t ul = (uint32_t)lane;
+  uint32_t ip = 0, op = 0;
+  while (true) {
+    if (ip >= in_n) return false;
+    if (ip + 32u <= in_n) {
+      // ---- window path
+      const uint32_t b = in[ip + ul];
+      const uint32_t tok = lz_pick(b, ul == 0u);
+      const uint32_t ll = tok >> 4;
+      if (ll < 15u) {                                              // 15 = extended literal length: generic path
+        uint32_t used = 3u + ll;                                   // token + literals + offset
+        const uint32_t off = lz_pick(ul == 2u + ll ? (b << 8) : b, ul == 1u + ll || ul == 2u + ll);
+        uint32_t ml = (tok & 15u) + 4u;
+        bool fits = true;
+        if ((tok & 15u) == 15u) {
+          const unsigned e = __ballot_sync(kFull, b != 255u) & ~((1u << used) - 1u);
+          if (e == 0u) fits = false;                               // extension runs past the window
+          else {
+            const uint32_t p = (uint32_t)__ffs(e) - 1u;
+            ml += 255u * (p - used) + lz_pick(b, ul == p);
+            used = p + 1u;
+          }
+        }
+        // period inside this sequence's literals?
+        if (fits && off <= ll && off <= 8u && (off & (off - 1u)) == 0u && off != 0u) {
+          if (ll > cap - op || ml > cap - op - ll) return false;
+          if (ul - 1u < ll) out[op + ul - 1u] = (uint8_t)b;       // literals: window lanes 1..ll
+          uint8_t* dst = out + op + ll;
+          // 8-byte period P: byte k = literal[ll - off + (k mod off)] = window lane 1 + ll - off + (k mod off)
+          const uint32_t pb = __shfl_sync(kFull, b, 1u + ll - off + (ul & (off - 1u)));
+          const uint32_t placed = pb << (8u * (ul & 3u));
+          const uint32_t plo = __reduce_or_sync(kFull, ul < 4u ? placed : 0u);
+          const uint32_t phi = __reduce_or_sync(kFull, (ul & 28u) == 4u ? placed : 0u);
+          // every 16-byte aligned vector of the run holds P rotated by (-dst) & 7 bytes, twice
+          const uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+          const uint32_t r0 = head & 7u;
+          const uint32_t wa = (r0 & 4u) ? phi : plo, wb = (r0 & 4u) ? plo : phi, sh = 8u * (r0 & 3u);
+          uint4 v;
+          v.x = __funnelshift_r(wa, wb, sh);
+          v.y = __funnelshift_r(wb, wa, sh);
+          v.z = v.x; v.w = v.y;
+          // byte j of the run, for lanes that write single bytes (j mod 8 selects a byte of P)
+          const uint32_t mine = (((ul & 4u) ? phi : plo) >> (8u * (ul & 3u))) & 0xffu;   // P[lane & 7]
+          if (ml < 16u + head) {
+            // short: bytes only (ml < 31)
+            if (ul < ml) dst[ul] = (uint8_t)mine;
+          } else {
+            if (ul < head) dst[ul] = (uint8_t)mine;
+            const uint32_t nvec = (ml - head) >> 4;
+            uint4* d16 = (uint4*)(dst + head);
+#pragma unroll 1
+            for (uint32_t k = ul; k < nvec; k += kWarp) st_v4(d16 + k, v);
+            // ragged end (< 16 bytes): position head + 16 nvec + lane; 16 nvec = 0 mod 8
+            const uint32_t j = head + (nvec << 4) + ul;
+            const uint32_t jb = (((j & 4u) ? phi : plo) >> (8u * (j & 3u))) & 0xffu;
+            if (j < ml) dst[j] = (uint8_t)jb;
+          }
+          op += ll + ml;
+          ip += used;
+          continue;
+        }
+      }
+    }
+    // ---- generic path: one sequence, field by field
+    const uint32_t tok = in[ip++];
+    uint32_t ll = tok >> 4;
+    if (ll == 15) { if (!lz4_read_ext(in, in_n, ip, ll, lane)) return false; }
+    if (ll > in_n - ip || ll > cap - op) return false;
+    if (ll) warp_copy<true>(out + op, in + ip, ll, lane);
+    ip += ll; op += ll;
+    if (ip >= in_n) break;                 // last sequence carries literals only
+    if (in_n - ip < 2) return false;
+    const uint32_t off = load_u16(in + ip);
+    ip += 2;
+    uint32_t ml = tok & 15u;
+    if (ml == 15) { if (!lz4_read_ext(in, in_n, ip, ml, lane)) return false; }
+    if (ml > 0xfffffff0u) return false;
+    ml += 4;
+    if (off == 0 || off > op || ml > cap - op) return false;
+    __syncwarp();                          // prior stores visible to all lanes
+    warp_match_copy(out + op, off, ml, lane);
+    __syncwarp();
+    op += ml;
+  }
+  *produced = op;
+  return true;
+}
+
 template <bool kWrite>
 __global__ void __launch_bounds__(128)
 lz4_decompress_kernel(const void* const* __restrict__ comp_ptrs,
@@ -151,7 +258,7 @@ __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t 
   // lane-parallel machinery only costs instructions there, so it is decoded by the direct
   // global-memory token loop (16-byte vector copies).  Dense short-token chunks take the
   // lane-parallel path.
-  if (out_cap >= 4ull * in_n) return lz4_decode_chunk<true>(in, in_n, out, out_cap, produced, lane);
+  if (out_cap >= 4ull * in_n) return lz4_decode_chunk_direct(in, in_n, out, out_cap, produced, lane);
   LzState s;
   s.in = in; s.in_n = in_n; s.out = out; s.out_cap = out_cap > 0xffffffffull ? 0xffffffffull : out_cap;
   s.ip = 0; s.op = 0; s.flushed = 0; s.ring_lo = 0;
