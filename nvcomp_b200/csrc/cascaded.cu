@@ -77,6 +77,25 @@ __device__ __forceinline__ uint32_t warp_incl_max_u32(uint32_t v, int lane) {
   return v;
 }
 
+// Inclusive warp scans of a lane total (add / max); the loops below block 4 consecutive elements per
+// lane, so one scan serves 128 elements.
+template <class S>
+__device__ __forceinline__ S warp_incl_scan(S v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const S o = __shfl_up_sync(kFull, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+template <int TS> struct ScanType { using S = uint32_t; };
+template <> struct ScanType<8> { using S = uint64_t; };
+
+// four consecutive elements of type T (16-byte vector accesses when 4*sizeof(T) >= 16)
+template <class T>
+struct alignas(sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4) Quad4 { T e[4]; };
+
 // typed smem element access with values carried as u64 (wrapping arithmetic)
 template <int TS> struct Elem;
 template <> struct Elem<1> { using T = uint8_t; };
@@ -183,24 +202,38 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
   const int L = R > D ? R : D;
   for (int i = L - 1; i >= 0; --i) {
     if (i < D) {
-      // undo delta i in place: cur[0..count) deltas -> cur[0..count] values (shifted by one; the
-      // next tile is loaded before this tile's stores).  cin == 0: the layer saw an empty list.
+      // undo delta i in place: cur[0..count) deltas -> cur[0..count] values.  cin == 0: the layer saw
+      // an empty list.
       const uint32_t c_in = cin[i];
       if (c_in == 0 && count != 0) return false;
       if (c_in != 0) {
         if (c_in != count + 1 || c_in > cap) return false;
-        uint64_t carry = firsts[i];
-        uint64_t vnext = ((uint32_t)lane < count) ? (uint64_t)cur[lane] : 0ull;
-        __syncwarp();
-        if (lane == 0) cur[0] = (T)carry;
-        for (uint32_t base = 0; base < count; base += kWarp) {
-          const uint32_t k = base + lane;
-          uint64_t v = vnext;
-          vnext = (k + kWarp < count) ? (uint64_t)cur[k + kWarp] : 0ull;
-          __syncwarp();
-          v = warp_incl_scan_u64(v, lane) + carry;
-          if (k < count) cur[k + 1] = (T)v;
-          carry = __shfl_sync(kFull, v, 31);
+        // Exclusive scan in place: out[k] = first + sum(d[0..k)), k = 0..count.  Each lane owns four
+        // consecutive elements (one vector load / store, one warp scan per 128 elements); element k
+        // is read and written by the same lane, so the pass needs no staging.
+        using S = typename ScanType<TS>::S;          // 32-bit wrapping sums suffice for <= 4-byte elements
+        S carry = (S)firsts[i];
+        const bool vec_ok = (cap & 3u) == 0u && ((uintptr_t)cur & 15u) == 0u;   // quads inside the buffer, aligned
+        for (uint32_t base = 0; base <= count; base += 4u * kWarp) {
+          const uint32_t k0 = base + 4u * (uint32_t)lane;
+          Quad4<T> q;
+          if (vec_ok && k0 < cap) q = *(const Quad4<T>*)(cur + k0);
+          else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q.e[e] = (k0 + e < cap) ? cur[k0 + e] : (T)0;
+          }
+          S d0 = (k0 + 0 < count) ? (S)q.e[0] : (S)0, d1 = (k0 + 1 < count) ? (S)q.e[1] : (S)0;
+          S d2 = (k0 + 2 < count) ? (S)q.e[2] : (S)0, d3 = (k0 + 3 < count) ? (S)q.e[3] : (S)0;
+          const S x1 = d0, x2 = d0 + d1, x3 = x2 + d2, tot = x3 + d3;
+          const S incl = warp_incl_scan<S>(tot, lane);
+          const S ex = incl - tot + carry;
+          q.e[0] = (T)ex; q.e[1] = (T)(ex + x1); q.e[2] = (T)(ex + x2); q.e[3] = (T)(ex + x3);
+          if (vec_ok && k0 + 3u <= count) *(Quad4<T>*)(cur + k0) = q;
+          else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (k0 + e <= count) cur[k0 + e] = q.e[e];
+          }
+          carry += __shfl_sync(kFull, incl, 31);
         }
         count += 1;
         __syncwarp();
@@ -220,34 +253,65 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
         for (uint32_t j = lane; j < (cap + 1) / 2; j += kWarp) z[j] = 0u;
       }
       __syncwarp();
+      // run starts: each lane owns four consecutive runs (one warp scan per 128 runs)
       uint32_t carry = 0;
       const bool narrow = rh.bits != 0u && rh.bits <= 32u;
       const uint32_t* rw32 = (const uint32_t*)rwords;
       const uint32_t rmask = rh.bits >= 32u ? 0xffffffffu : ((1u << rh.bits) - 1u);
-      for (uint32_t base = 0; base < count; base += kWarp) {
-        const uint32_t k = base + lane;
-        uint32_t len = 0u;
-        if (k < count)
-          len = narrow ? (uint32_t)unpack32_at(rw32, k, rh.bits, rmask, rh.minv)
-                       : (uint32_t)unpack_at(rwords, k, rh.bits, rh.minv);
-        const uint32_t incl = warp_incl_scan_u32(len, lane) + carry;
-        carry = __shfl_sync(kFull, incl, 31);
+      for (uint32_t base = 0; base < count; base += 4u * kWarp) {
+        const uint32_t k0 = base + 4u * (uint32_t)lane;
+        uint32_t len[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t l = 0u;
+          if (k0 + e < count)
+            l = narrow ? (uint32_t)unpack32_at(rw32, k0 + e, rh.bits, rmask, rh.minv)
+                       : (uint32_t)min((unsigned long long)unpack_at(rwords, k0 + e, rh.bits, rh.minv), (unsigned long long)cap + 1ull);
+          len[e] = min(l, cap + 1u);                    // no wrap-around in the sums below
+        }
+        const uint32_t p1 = len[0], p2 = p1 + len[1], p3 = p2 + len[2], tot = p3 + len[3];
+        const uint32_t incl = warp_incl_scan<uint32_t>(tot, lane);
+        const uint32_t ex = incl - tot + carry;
+        carry += __shfl_sync(kFull, incl, 31);
         if (carry > cap) return false;
-        if (k < count && len != 0u) idx[incl - len] = (uint16_t)k;
+        if (k0 + 0 < count && len[0]) idx[ex] = (uint16_t)(k0 + 0);
+        if (k0 + 1 < count && len[1]) idx[ex + p1] = (uint16_t)(k0 + 1);
+        if (k0 + 2 < count && len[2]) idx[ex + p2] = (uint16_t)(k0 + 2);
+        if (k0 + 3 < count && len[3]) idx[ex + p3] = (uint16_t)(k0 + 3);
       }
       const uint32_t total = carry;
       if (total > cap || total < count) return false;
       if (last && total != n_out) return false;
       __syncwarp();
-      // run index per output element via max-scan, then gather
+      // run index of every output element: running maximum of the head flags, four consecutive
+      // elements per lane (one warp max-scan per 128 outputs), written back over the flags ...
       uint32_t mcarry = 0;
-      for (uint32_t base = 0; base < total; base += kWarp) {
-        const uint32_t j = base + lane;
-        uint32_t r = (j < total) ? (uint32_t)idx[j] : 0u;
-        r = max(warp_incl_max_u32(r, lane), mcarry);
-        if (j < total) dst[j] = cur[r];
-        mcarry = __shfl_sync(kFull, r, 31);
+      const bool ivec = ((uintptr_t)idx & 7u) == 0u;
+      for (uint32_t base = 0; base < total; base += 4u * kWarp) {
+        const uint32_t j0 = base + 4u * (uint32_t)lane;
+        Quad4<uint16_t> q;
+        if (ivec && j0 < (cap & ~3u)) q = *(const Quad4<uint16_t>*)(idx + j0);
+        else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) q.e[e] = (j0 + e < cap) ? idx[j0 + e] : (uint16_t)0;
+        }
+        const uint32_t m0 = q.e[0], m1 = max(m0, (uint32_t)q.e[1]), m2 = max(m1, (uint32_t)q.e[2]),
+                       m3 = max(m2, (uint32_t)q.e[3]);
+        const uint32_t incl = warp_incl_max_u32(m3, lane);
+        uint32_t ex = __shfl_up_sync(kFull, incl, 1);
+        ex = max(lane ? ex : 0u, mcarry);
+        q.e[0] = (uint16_t)max(ex, m0); q.e[1] = (uint16_t)max(ex, m1);
+        q.e[2] = (uint16_t)max(ex, m2); q.e[3] = (uint16_t)max(ex, m3);
+        if (ivec && j0 < (cap & ~3u)) *(Quad4<uint16_t>*)(idx + j0) = q;
+        else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (j0 + e < cap) idx[j0 + e] = q.e[e];
+        }
+        mcarry = max(mcarry, __shfl_sync(kFull, incl, 31));
       }
+      __syncwarp();
+      // ... then a coalesced gather: consecutive lanes write consecutive outputs
+      for (uint32_t j = lane; j < total; j += kWarp) dst[j] = cur[idx[j]];
       if (last) return true;
       count = total;
       __syncwarp();
