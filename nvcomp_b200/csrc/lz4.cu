@@ -83,8 +83,9 @@ __device__ __forceinline__ bool lz4_decode_chunk(const uint8_t* __restrict__ in,
 // so the token loop's control flow is provably uniform.  A match whose period (1, 2, 4 or 8 bytes) lies
 // inside the literals of its own sequence -- the shape of typed run-length data -- is expanded from the
 // window: the 8-byte period is rotated to the destination alignment and broadcast with 16-byte stores,
-// no load from the output buffer.  Everything else (other matches, sequences that do not fit the
-// window, the end of the block) takes the generic field-by-field path below.
+// no load from the output buffer.  Other matches are copied through memory (common.cuh) with the fields
+// already in registers; sequences that do not fit the window (long literal runs, far length
+// extensions, the end of the block) take the generic field-by-field path below.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lz_pick(uint32_t b, bool mine) {     // the byte of the lane(s) where `mine`
   return __reduce_or_sync(kFull, mine ? b : 0u);
@@ -118,11 +119,20 @@ __device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restric
             used = p + 1u;
           }
         }
-        // period inside this sequence's literals?
-        if (fits && off <= ll && off <= 8u && (off & (off - 1u)) == 0u && off != 0u) {
-          if (ll > cap - op || ml > cap - op - ll) return false;
+        if (fits) {
+          if (ll > cap - op || ml > cap - op - ll || off == 0u || off > op + ll) return false;
           if (ul - 1u < ll) out[op + ul - 1u] = (uint8_t)b;       // literals: window lanes 1..ll
           uint8_t* dst = out + op + ll;
+          if (!(off <= ll && off <= 8u && (off & (off - 1u)) == 0u)) {
+            // general match: copy through memory (fields came from the window, no further input loads)
+            __syncwarp();
+            warp_match_copy(dst, off, ml, lane);
+            __syncwarp();
+            op += ll + ml;
+            ip += used;
+            continue;
+          }
+          // period (1, 2, 4 or 8 bytes) inside this sequence's literals: expand from the window
           // 8-byte period P: byte k = literal[ll - off + (k mod off)] = window lane 1 + ll - off + (k mod off)
           const uint32_t pb = __shfl_sync(kFull, b, 1u + ll - off + (ul & (off - 1u)));
           const uint32_t placed = pb << (8u * (ul & 3u));
