@@ -194,6 +194,10 @@ __device__ __forceinline__ void warp_match_copy(uint8_t* dst, uint32_t off, uint
       if (j < len) dst[j] = src[j & (off - 1)];
       return;
     }
+    if (pow2) {                                   // short periodic run: j mod off is a mask
+      for (uint32_t j = lane; j < len; j += kWarp) dst[j] = src[j & (off - 1)];
+      return;
+    }
     uint32_t r = (uint32_t)lane % off;
     const uint32_t step = 32u % off;
     for (uint32_t j = lane; j < len; j += kWarp) {

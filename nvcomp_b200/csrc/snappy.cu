@@ -66,22 +66,25 @@ __device__ __forceinline__ bool snappy_decode_chunk(const uint8_t* __restrict__ 
       len = (tag >> 2) + 1;
       off = load_u16(in + ip);
       ip += 2;
-      // a run of copy-2 elements with the same offset is one long match (64 bytes per element):
-      // lane i inspects element i, the run is merged and copied once
-      const uint32_t q = ip + 3u * (uint32_t)lane;
-      uint32_t flen = 0;
-      bool same = false;
-      if (q + 3u <= in_n) {
-        const uint32_t t2 = in[q];
-        same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
-        flen = (t2 >> 2) + 1;
-      }
-      const unsigned m = __ballot_sync(kFull, same);
-      const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
-      uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
+      // a run of copy-2 elements with the same offset is one long match (64 bytes per element, so
+      // only a full-length element can have a continuation): lane i inspects element i, the run is
+      // merged and copied once
+      if (len == 64u) {
+        const uint32_t q = ip + 3u * (uint32_t)lane;
+        uint32_t flen = 0;
+        bool same = false;
+        if (q + 3u <= in_n) {
+          const uint32_t t2 = in[q];
+          same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
+          flen = (t2 >> 2) + 1;
+        }
+        const unsigned m = __ballot_sync(kFull, same);
+        const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
+        uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
 #pragma unroll
-      for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
-      if (len <= n_out - op && add <= n_out - op - len) { len += add; ip += 3u * nf; }
+        for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
+        if (len <= n_out - op && add <= n_out - op - len) { len += add; ip += 3u * nf; }
+      }
     } else {
       if (in_n - ip < 4) return false;
       len = (tag >> 2) + 1;
@@ -141,21 +144,24 @@ struct SnappyDecode : SnappyPolicy {
       len = (tag >> 2) + 1;
       off = load_u16(in + ip);
       ip += 2;
-      // merge following copy-2 elements with the same offset (lane i inspects element i)
-      const uint32_t q = ip + 3u * (uint32_t)lane;
-      uint32_t flen = 0;
-      bool same = false;
-      if (q + 3u <= in_n) {
-        const uint32_t t2 = in[q];
-        same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
-        flen = (t2 >> 2) + 1;
-      }
-      const unsigned m = __ballot_sync(kFull, same);
-      const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
-      uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
+      // merge following copy-2 elements with the same offset (lane i inspects element i); only a
+      // full-length element can have a continuation
+      if (len == 64u) {
+        const uint32_t q = ip + 3u * (uint32_t)lane;
+        uint32_t flen = 0;
+        bool same = false;
+        if (q + 3u <= in_n) {
+          const uint32_t t2 = in[q];
+          same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
+          flen = (t2 >> 2) + 1;
+        }
+        const unsigned m = __ballot_sync(kFull, same);
+        const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
+        uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
 #pragma unroll
-      for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
-      if (add <= n_out - s.op - min(len, n_out - s.op)) { len += add; ip += 3u * nf; }
+        for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
+        if (add <= n_out - s.op - min(len, n_out - s.op)) { len += add; ip += 3u * nf; }
+      }
     } else {
       if (in_n - ip < 4) return -1;
       len = (tag >> 2) + 1;
