@@ -112,6 +112,10 @@ __device__ __forceinline__ bool btc_read_header(const uint8_t* in, size_t in_byt
   return true;
 }
 
+// four consecutive elements (16-byte vector stores when 4*sizeof(T) >= 16)
+template <class T>
+struct alignas(sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4) BtcQuad { T e[4]; };
+
 template <int TS>
 __device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const uint8_t* __restrict__ payload,
                                                  typename BtcElem<TS>::T* out, uint32_t n_valid, int lane) {
@@ -121,44 +125,71 @@ __device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const 
   if (algo == 0) {
     const uint32_t bits = desc & 0xffu;
     const uint64_t first = p64[0];
-    uint64_t sum = 0;
     if (bits <= 16u) {
-      // the lane's four values span at most 64 + 63 bits: two word loads, then shifts
-      // (bits is uniform over the block, so this branch does not diverge)
-      const uint32_t bitpos = 4u * (uint32_t)lane * bits;
-      const uint32_t w0 = bitpos >> 6, s0 = bitpos & 63u;
-      uint64_t lo = 0, hi = 0;
-      if (bits) {
-        lo = p64[1 + w0];
-        if (s0 + 4u * bits > 64u) hi = p64[2 + w0];
-      }
-      const uint64_t mask = (1ull << bits) - 1ull;
+      // Small deltas (the common case for sorted / smooth columns): the zigzag codes fit 16 bits, so
+      // the lane-local prefix and the warp scan run in 32-bit arithmetic (|sum of 128 deltas| < 2^23);
+      // only the final "first + prefix" is 64-bit.  bits is uniform over the block: no divergence.
+      uint32_t z[4];
+      if (bits <= 8u) {
+        // the lane's four codes lie inside 32 bits: one or two 32-bit words and a funnel shift
+        const uint32_t* p32 = (const uint32_t*)(p64 + 1);
+        const uint32_t bitpos = 4u * (uint32_t)lane * bits;
+        const uint32_t w0 = bitpos >> 5, s0 = bitpos & 31u;
+        uint32_t lo = 0, hi = 0;
+        if (bits) {
+          lo = p32[w0];
+          if (s0 + 4u * bits > 32u) hi = p32[w0 + 1];
+        }
+        const uint32_t x = __funnelshift_r(lo, hi, s0);
+        const uint32_t mask = (1u << bits) - 1u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t sj = s0 + (uint32_t)j * bits;          // < 128
-        uint64_t z;
-        if (sj < 64u) z = (lo >> sj) | (sj ? (hi << (64u - sj)) : 0ull);
-        else z = hi >> (sj - 64u);
-        sum += btc_unzigzag(z & mask);
-        v[j] = sum;
+        for (int j = 0; j < 4; ++j) z[j] = (x >> ((uint32_t)j * bits)) & mask;
+      } else {
+        // four codes span at most 64 + 63 bits: two 64-bit word loads, then shifts
+        const uint32_t bitpos = 4u * (uint32_t)lane * bits;
+        const uint32_t w0 = bitpos >> 6, s0 = bitpos & 63u;
+        const uint64_t lo = p64[1 + w0];
+        const uint64_t hi = (s0 + 4u * bits > 64u) ? p64[2 + w0] : 0ull;
+        const uint64_t mask = (1ull << bits) - 1ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t sj = s0 + (uint32_t)j * bits;          // < 128
+          uint64_t zz;
+          if (sj < 64u) zz = (lo >> sj) | (sj ? (hi << (64u - sj)) : 0ull);
+          else zz = hi >> (sj - 64u);
+          z[j] = (uint32_t)(zz & mask);
+        }
       }
+      uint32_t pre[4], acc = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc += (z[j] >> 1) ^ (0u - (z[j] & 1u)); pre[j] = acc; }
+      uint32_t incl = acc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const uint32_t base = incl - acc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = first + (uint64_t)(int64_t)(int32_t)(base + pre[j]);
     } else {
+      uint64_t sum = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint64_t z = btc_unpack(p64 + 1, 4 * lane + j, bits);
         sum += btc_unzigzag(z);
         v[j] = sum;
       }
-    }
-    uint64_t incl = sum;
+      uint64_t incl = sum;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint64_t o = __shfl_up_sync(kFull, incl, d);
-      if (lane >= d) incl += o;
-    }
-    const uint64_t base = first + incl - sum;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t o = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const uint64_t base = first + incl - sum;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] += base;
+      for (int j = 0; j < 4; ++j) v[j] += base;
+    }
   } else {
     const uint32_t bits = desc >> 8;
     const uint64_t mlo = p64[0], mhi = p64[1];
@@ -175,9 +206,17 @@ __device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const 
     }
   }
   const uint32_t e = 4 * lane;
+  // the lane's four consecutive elements leave as one vector store when the chunk pointer allows it
+  BtcQuad<T> q;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (e + j < n_valid) out[e + j] = (T)v[j];
+  for (int j = 0; j < 4; ++j) q.e[j] = (T)v[j];
+  if (e + 3u < n_valid && ((uintptr_t)out & (alignof(BtcQuad<T>) - 1)) == 0) {
+    *(BtcQuad<T>*)(out + e) = q;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e + j < n_valid) out[e + j] = q.e[j];
+  }
 }
 
 __global__ void __launch_bounds__(kBtcThreads)
