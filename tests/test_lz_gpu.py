@@ -197,3 +197,70 @@ def test_ragged_and_empty_batch(oracle):
         # batch of zero chunks is a no-op
         from nvcomp_b200.batched import _stream_handle
         codec.decompress_async(None, None, None, None, 0, None, 0, None, None, _stream_handle(None))
+
+
+def _lz4_block(seqs, tail_literals):
+    """Assemble an LZ4 block from (literals, offset, match_len) sequences + the final literal-only sequence;
+    returns (block, expected_output)."""
+    def ext(n):
+        out = bytearray()
+        while n >= 255:
+            out.append(255); n -= 255
+        out.append(n)
+        return bytes(out)
+    blk, out = bytearray(), bytearray()
+    for lits, off, ml in seqs:
+        ll, mc = len(lits), ml - 4
+        blk.append((min(ll, 15) << 4) | min(mc, 15))
+        if ll >= 15:
+            blk += ext(ll - 15)
+        blk += lits
+        blk += bytes([off & 255, off >> 8])
+        if mc >= 15:
+            blk += ext(mc - 15)
+        out += lits
+        assert 1 <= off <= len(out)
+        for _ in range(ml):
+            out.append(out[-off])
+    ll = len(tail_literals)
+    blk.append(min(ll, 15) << 4)
+    if ll >= 15:
+        blk += ext(ll - 15)
+    blk += tail_literals
+    out += tail_literals
+    return bytes(blk), bytes(out)
+
+
+@pytest.mark.parametrize("misalign", [0, 1, 5, 8, 15])
+def test_lz4_register_window_sequences(misalign, liblz4):
+    """Hand-assembled high-ratio LZ4 blocks aimed at the direct decoder's register-window path: periods
+    1/2/4/8 inside the sequence's literals (expanded from registers), the same periods reaching behind the
+    literals, non-power-of-two and long periods (memory copy), literal counts 0..14 and 15+ (extension),
+    match lengths on both sides of every internal threshold, length extensions that end inside / beyond the
+    32-byte window.  Checked against liblz4 and the byte-serial expansion."""
+    from gpu_util import gpu_decompress
+    rng = np.random.default_rng(99)
+    lens = [4, 5, 15, 18, 19, 20, 30, 31, 32, 33, 47, 63, 64, 65, 100, 273, 274, 500, 529, 4000, 7000, 9000]
+    chunks, expect = [], []
+    for period in [1, 2, 4, 8, 3, 5, 7, 12, 16, 40]:
+        seqs = []
+        first = True
+        for i, ml in enumerate(lens):
+            for ll in ([period, period + 1, 14] if period <= 13 else [14, 20]):
+                lits = rng.integers(0, 256, ll, dtype=np.uint8).tobytes()
+                if first and ll < period:
+                    lits = rng.integers(0, 256, period, dtype=np.uint8).tobytes()
+                seqs.append((lits, period, ml))
+                first = False
+            seqs.append((b"", period, ml))                       # no literals: period reaches behind
+            seqs.append((rng.integers(0, 256, 2, dtype=np.uint8).tobytes(), period, ml))
+        seqs.append((rng.integers(0, 256, 40, dtype=np.uint8).tobytes(), 8, 1000))   # 15+ literals
+        blk, out = _lz4_block(seqs, b"tail-literals")
+        assert len(out) >= 4 * len(blk)                          # routed to the direct decoder
+        assert liblz4.decompress(blk, len(out)) == out
+        chunks.append(blk); expect.append(out)
+    outs, actual, status, _ = gpu_decompress(_codec("lz4"), chunks, [len(e) for e in expect], misalign=misalign)
+    assert (status == 0).all(), status
+    assert actual.tolist() == [len(e) for e in expect]
+    for i, (o, e) in enumerate(zip(outs, expect)):
+        assert o == e, i

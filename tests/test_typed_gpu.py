@@ -55,7 +55,7 @@ def test_cascaded(oracle, type_id, layers):
     _roundtrip(codec, "cascaded", _raws(8), oracle, dict(type=type_id, num_RLEs=r, num_deltas=d, use_bp=bp))
 
 
-@pytest.mark.parametrize("part", [512, 1024, 8192, 16384])
+@pytest.mark.parametrize("part", [512, 520, 1000, 1024, 8192, 16384])     # 520, 1000: element counts not divisible by 4
 def test_cascaded_partition_sizes(oracle, part):
     from nvcomp_b200._lib import CascadedOpts
     from nvcomp_b200.batched import Codec
@@ -166,3 +166,62 @@ def test_maximum_chunk_size(kind, oracle):
     assert (status == 0).all() and outs == raws
     with pytest.raises(NvcompError):
         codec.compress_get_max_output_chunk_size((1 << 24) + 1)
+
+
+@pytest.mark.parametrize("type_id", sorted(TS))
+def test_bitcomp_delta_width_sweep(oracle, type_id):
+    """Blocks whose zig-zag delta width runs from 0 to the full type width hit every decode path (<= 8 bits:
+    32-bit funnel unpack; 9..16: 64-bit unpack with 32-bit prefix; > 16: 64-bit), with ragged last blocks and
+    chunk pointers that are 8- but not 16-byte aligned (scalar instead of vector stores)."""
+    from gpu_util import gpu_compress, gpu_decompress
+    from nvcomp_b200._lib import BitcompOpts
+    from nvcomp_b200.batched import Codec
+    ts = TS[type_id]
+    dt = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[ts]
+    rng = np.random.default_rng(5 + type_id)
+    raws = []
+    for n in [1, 127, 128, 129, 1000, 8192]:
+        parts = []
+        for k in range(0, min(8 * ts, 62)):             # one 128-element block per delta magnitude 2^k
+            step = rng.integers(-(1 << k), (1 << k) + 1, 128).astype(np.int64)
+            parts.append(step)
+        steps = np.concatenate(parts)[: max(n, 1)]
+        if n > len(steps):
+            steps = np.resize(steps, n)
+        vals = (np.cumsum(steps) + int(rng.integers(0, 1 << 20))).astype(np.int64).astype(dt)
+        raws.append(vals.tobytes())
+    codec = Codec("Bitcomp", opts=BitcompOpts(0, type_id))
+    for mis in (0, 8):
+        comps, _ = gpu_compress(codec, raws, misalign=mis)
+        for c, r in zip(comps, raws):
+            assert oracle.decompress("bitcomp", c, len(r)) == r
+        outs, actual, status, _ = gpu_decompress(codec, comps, [len(r) for r in raws], misalign=mis)
+        assert (status == 0).all(), status
+        assert outs == raws
+        ocomps = [oracle.compress_typed("bitcomp", r, algo=0, type=type_id) for r in raws]
+        outs, actual, status, _ = gpu_decompress(codec, ocomps, [len(r) for r in raws], misalign=mis)
+        assert (status == 0).all() and outs == raws
+
+
+def test_ans_entropy_and_segment_edges(oracle):
+    """ANS streams from ~0.5 to ~7.5 bits/byte (few to many renormalisation words per round: the word ring
+    is refilled one block every few groups up to several blocks per group) at sizes around the 32-symbol
+    round and the 16384-symbol segment."""
+    from gpu_util import gpu_compress, gpu_decompress
+    from nvcomp_b200.batched import Codec
+    rng = np.random.default_rng(77)
+    raws = []
+    for p in [0.9, 0.5, 0.2, 0.05, 0.02, 0.008]:                 # geometric symbol distributions
+        for n in [1, 31, 32, 33, 1000, 16383, 16384, 16385, 50000, 65536]:
+            raws.append(np.minimum(rng.geometric(p, n) - 1, 255).astype(np.uint8).tobytes())
+    raws.append(bytes([7]) * 40000)                              # constant chunk
+    codec = Codec("ANS")
+    comps, _ = gpu_compress(codec, raws)
+    for c, r in zip(comps, raws):
+        assert oracle.decompress("ans", c, len(r)) == r
+    outs, actual, status, _ = gpu_decompress(codec, comps, [len(r) for r in raws])
+    assert (status == 0).all(), status
+    assert outs == raws
+    ocomps = [oracle.compress_typed("ans", r) for r in raws]
+    outs, actual, status, _ = gpu_decompress(codec, ocomps, [len(r) for r in raws])
+    assert (status == 0).all() and outs == raws
