@@ -52,22 +52,6 @@ __host__ __device__ inline bool casc_type_signed(int t) {
   return t == NVCOMP_TYPE_CHAR || t == NVCOMP_TYPE_SHORT || t == NVCOMP_TYPE_INT || t == NVCOMP_TYPE_LONGLONG;
 }
 
-__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint64_t o = __shfl_up_sync(kFull, v, d);
-    if (lane >= d) v += o;
-  }
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(kFull, v, d);
-    if (lane >= d) v += o;
-  }
-  return v;
-}
 __device__ __forceinline__ uint32_t warp_incl_max_u32(uint32_t v, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {

@@ -7,8 +7,9 @@
 //
 // Decode: one warp owns one chunk; chunks are handed out by a persistent two-pass ticket
 // scheduler (dense chunks first).  Dense short-token chunks use the lane-parallel decoder of
-// lz_decode.cuh; chunks that compressed >= 4x use the direct token loop below (warp-uniform
-// parse, 16-byte vector copies: common.cuh warp_copy / warp_match_copy).
+// lz_decode.cuh; chunks that compressed >= 4x use the direct sequence loop below (the sequence is
+// parsed from a 32-byte register window, run-length matches are expanded from registers, other
+// matches are 16-byte vector copies: common.cuh warp_copy / warp_match_copy).
 #include "common.cuh"
 #include "lz77_compress.cuh"
 #include "lz_decode.cuh"
@@ -35,12 +36,10 @@ __device__ __forceinline__ bool lz4_read_ext(const uint8_t* __restrict__ in, uin
   }
 }
 
-// Decode one LZ4 block.  kWrite=false only walks the tokens (size query).
-// Returns true on success; *produced receives the decompressed size.
-template <bool kWrite>
-__device__ __forceinline__ bool lz4_decode_chunk(const uint8_t* __restrict__ in, uint32_t in_n,
-                                                 uint8_t* out, uint64_t out_cap,
-                                                 uint32_t* produced, int lane) {
+// Walk the sequences of one LZ4 block without copying (size query: LZ4 blocks carry no size header).
+// Returns true on a well-formed block; *produced receives the decompressed size.
+__device__ __forceinline__ bool lz4_walk_chunk(const uint8_t* __restrict__ in, uint32_t in_n,
+                                               uint32_t* produced, int lane) {
   uint32_t ip = 0;
   uint64_t op = 0;
   if (in_n == 0) { *produced = 0; return true; }
@@ -50,10 +49,6 @@ __device__ __forceinline__ bool lz4_decode_chunk(const uint8_t* __restrict__ in,
     uint32_t ll = tok >> 4;
     if (ll == 15) { if (!lz4_read_ext(in, in_n, ip, ll, lane)) return false; }
     if (ll > in_n - ip) return false;
-    if (kWrite) {
-      if ((uint64_t)ll > out_cap - op) return false;
-      if (ll) warp_copy<true>(out + op, in + ip, ll, lane);
-    }
     ip += ll; op += ll;
     if (ip >= in_n) break;                 // last sequence carries literals only
     if (in_n - ip < 2) return false;
@@ -63,12 +58,6 @@ __device__ __forceinline__ bool lz4_decode_chunk(const uint8_t* __restrict__ in,
     if (ml == 15) { if (!lz4_read_ext(in, in_n, ip, ml, lane)) return false; }
     ml += 4;
     if (off == 0 || (uint64_t)off > op) return false;
-    if (kWrite) {
-      if ((uint64_t)ml > out_cap - op) return false;
-      __syncwarp();                        // prior stores visible to all lanes
-      warp_match_copy(out + op, off, ml, lane);
-      __syncwarp();
-    }
     op += ml;
     if (op > 0xffffffffull) return false;
   }
@@ -193,31 +182,20 @@ __device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restric
   return true;
 }
 
-template <bool kWrite>
+// Size query: one warp walks one chunk.
 __global__ void __launch_bounds__(128)
-lz4_decompress_kernel(const void* const* __restrict__ comp_ptrs,
-                      const size_t* __restrict__ comp_bytes,
-                      const size_t* __restrict__ out_caps,
-                      size_t* actual_bytes, size_t batch,
-                      void* const* __restrict__ out_ptrs,
-                      nvcompStatus_t* statuses,
-                      unsigned long long* ticket) {
+lz4_size_kernel(const void* const* __restrict__ comp_ptrs, const size_t* __restrict__ comp_bytes,
+                size_t* out_sizes, size_t batch) {
   const int lane = lane_id();
   const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
-  WarpTicket sched(ticket, warp_global, warps_total);
-  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+  for (size_t c = warp_global; c < batch; c += warps_total) {
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     const size_t in_n64 = comp_bytes[c];
-    uint8_t* out = kWrite ? (uint8_t*)out_ptrs[c] : nullptr;
-    const uint64_t cap = kWrite ? (uint64_t)out_caps[c] : ~0ull;
     uint32_t produced = 0;
     bool ok = in_n64 <= 0xffffffffull;
-    if (ok) ok = lz4_decode_chunk<kWrite>(in, (uint32_t)in_n64, out, cap, &produced, lane);
-    if (lane == 0) {
-      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
-      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
-    }
+    if (ok) ok = lz4_walk_chunk(in, (uint32_t)in_n64, &produced, lane);
+    if (lane == 0) out_sizes[c] = ok ? (size_t)produced : 0;
   }
 }
 
@@ -467,8 +445,7 @@ nvcompStatus_t nvcompBatchedLZ4GetDecompressSizeAsync(
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_sizes) return nvcompErrorInvalidValue;
   const int grid = persistent_grid(8, batch, 4);
-  lz4_decompress_kernel<false><<<grid, 128, 0, stream>>>(
-      comp_ptrs, comp_bytes, nullptr, out_sizes, batch, nullptr, nullptr, nullptr);
+  lz4_size_kernel<<<grid, 128, 0, stream>>>(comp_ptrs, comp_bytes, out_sizes, batch);
   B200_CUDA_TRY(cudaGetLastError());
   return nvcompSuccess;
 }
