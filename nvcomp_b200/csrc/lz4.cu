@@ -68,18 +68,13 @@ __device__ __forceinline__ bool lz4_walk_chunk(const uint8_t* __restrict__ in, u
 // ---------------------------------------------------------------------------
 // Direct decode for chunks that compressed >= 4x (long matches, typed run-length data).  One coalesced
 // 32-byte load brings a whole sequence (token, short literals, offset, length-extension bytes) into a
-// register window; fields are extracted with warp OR-reductions, whose results are uniform registers,
-// so the token loop's control flow is provably uniform.  A match whose period (1, 2, 4 or 8 bytes) lies
+// register window; fields are picked with shuffles / a ballot.  A match whose period (1, 2, 4 or 8 bytes) lies
 // inside the literals of its own sequence -- the shape of typed run-length data -- is expanded from the
 // window: the 8-byte period is rotated to the destination alignment and broadcast with 16-byte stores,
 // no load from the output buffer.  Other matches are copied through memory (common.cuh) with the fields
 // already in registers; sequences that do not fit the window (long literal runs, far length
 // extensions, the end of the block) take the generic field-by-field path below.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lz_pick(uint32_t b, bool mine) {     // the byte of the lane(s) where `mine`
-  return __reduce_or_sync(kFull, mine ? b : 0u);
-}
-
 __device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restrict__ in, uint32_t in_n,
                                                         uint8_t* out, uint64_t out_cap64,
                                                         uint32_t* produced, int lane) {
@@ -92,11 +87,11 @@ __device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restric
     if (ip + 32u <= in_n) {
       // ---- window path
       const uint32_t b = in[ip + ul];
-      const uint32_t tok = lz_pick(b, ul == 0u);
+      const uint32_t tok = __shfl_sync(kFull, b, 0);
       const uint32_t ll = tok >> 4;
       if (ll < 15u) {                                              // 15 = extended literal length: generic path
         uint32_t used = 3u + ll;                                   // token + literals + offset
-        const uint32_t off = lz_pick(ul == 2u + ll ? (b << 8) : b, ul == 1u + ll || ul == 2u + ll);
+        const uint32_t off = __shfl_sync(kFull, b, 1 + ll) | (__shfl_sync(kFull, b, 2 + ll) << 8);
         uint32_t ml = (tok & 15u) + 4u;
         bool fits = true;
         if ((tok & 15u) == 15u) {
@@ -104,7 +99,7 @@ __device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restric
           if (e == 0u) fits = false;                               // extension runs past the window
           else {
             const uint32_t p = (uint32_t)__ffs(e) - 1u;
-            ml += 255u * (p - used) + lz_pick(b, ul == p);
+            ml += 255u * (p - used) + __shfl_sync(kFull, b, p);
             used = p + 1u;
           }
         }
@@ -144,8 +139,11 @@ __device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restric
             if (ul < head) dst[ul] = (uint8_t)mine;
             const uint32_t nvec = (ml - head) >> 4;
             uint4* d16 = (uint4*)(dst + head);
+            // nvec <= 64 for matches up to ~1 KB: two predicated stores, a loop only beyond that
+            if (ul < nvec) st_v4(d16 + ul, v);
+            if (ul + kWarp < nvec) st_v4(d16 + ul + kWarp, v);
 #pragma unroll 1
-            for (uint32_t k = ul; k < nvec; k += kWarp) st_v4(d16 + k, v);
+            for (uint32_t k = ul + 2u * kWarp; k < nvec; k += kWarp) st_v4(d16 + k, v);
             // ragged end (< 16 bytes): position head + 16 nvec + lane; 16 nvec = 0 mod 8
             const uint32_t j = head + (nvec << 4) + ul;
             const uint32_t jb = (((j & 4u) ? phi : plo) >> (8u * (j & 3u))) & 0xffu;
