@@ -14,7 +14,15 @@ ORACLE_LIB  := oracle/liboracle.so
 
 TESTS_BIN := build/tests/hlif_test
 
-all: $(LIB) $(ORACLE_LIB) $(TESTS_BIN)
+# host warp emulator (test infrastructure): the warp-level decode headers compiled with g++, PTX shadowed
+EMU_LIB  := tests/emu/libemu_lz.so
+EMU_SRCS := tests/emu/emu_cuda.cpp tests/emu/emu_lz.cpp
+
+all: $(LIB) $(ORACLE_LIB) $(TESTS_BIN) $(EMU_LIB)
+
+$(EMU_LIB): $(EMU_SRCS) $(wildcard tests/emu/*.h) $(wildcard tests/emu/*.cuh) $(HDRS)
+	g++ -std=c++17 -O2 -g -fPIC -shared -Wall -Wno-unknown-pragmas -Wno-unused-function \
+	    -Itests/emu -I$(SRC_DIR) -Iinclude -I/usr/local/cuda/include $(EMU_SRCS) -o $@
 
 $(BUILD_DIR)/%.o: $(SRC_DIR)/%.cu $(HDRS)
 	@mkdir -p $(BUILD_DIR)

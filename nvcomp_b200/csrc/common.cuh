@@ -9,6 +9,7 @@
 #include <stddef.h>
 
 #include "nvcomp/shared_types.h"
+#include <ptx.cuh>   // found through -I (csrc/ for the library; tests/emu shadows it for the host emulator)
 
 namespace b200 {
 
@@ -44,29 +45,6 @@ struct WarpTicket {
     return (size_t)__shfl_sync(kFull, t, 0);
   }
 };
-
-// ---------------------------------------------------------------------------
-// Global-memory access helpers.
-// ---------------------------------------------------------------------------
-// Read-only, streaming (compressed input is read once): bypass L1 allocation.
-__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-// Streaming store: decompressed output is written once, never re-read by this
-// kernel beyond the match window, so do not let it thrash L1.
-__device__ __forceinline__ void st_v4(uint4* p, const uint4& v) {
-  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};"
-               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_v4(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-  return r;
-}
 
 // Unaligned little-endian loads from byte pointers (no alignment assumed).
 __device__ __forceinline__ uint32_t load_u16(const uint8_t* p) {
@@ -217,39 +195,6 @@ __device__ __forceinline__ void warp_match_copy(uint8_t* dst, uint32_t off, uint
     span <<= 1;
     __syncwarp();
   }
-}
-
-// ---------------------------------------------------------------------------
-// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: one thread stages a
-// 16-byte aligned span of global memory into shared memory asynchronously; consumers wait on
-// the mbarrier's phase.  Addresses are 32-bit shared-window addresses.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" :: "r"(mbar), "r"(parity) : "memory");
-}
-// order this thread's earlier generic-proxy accesses to shared memory before later async-proxy writes
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-// smem_dst, gmem_src and bytes must be multiples of 16
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
 }
 
 // Host-side launch helper: number of CTAs for a persistent kernel.

@@ -1,15 +1,12 @@
-// lz_decode.cuh -- lane-parallel LZ77 (LZ4 / Snappy) chunk decoder for B200.
+// lz_decode.cuh -- block-parallel LZ77 (LZ4 / Snappy) chunk decoder for B200.
 //
 // One warp owns one chunk.  On tabular data a 64 KB chunk holds 10-15 thousand *short* tokens
-// (4-8 output bytes each), so throughput is bounded by warp-instructions per token, not bytes:
+// (4-8 output bytes each), so throughput is bounded by warp-instructions per token, not bytes.
 //
-//  * FAST PATH (short tokens, lz_fast_iter).  The 32 lanes look at 32 consecutive input bytes.
-//    Every lane parses the byte under it as if it were a token start (speculative parse), the true
-//    token chain is recovered with 4 rounds of pointer doubling (__reduce_or_sync + __shfl_sync), a
-//    warp scan of the token output lengths gives every token its output position, literals are
-//    scattered in one pass straight from registers, matches whose sources are already final are
-//    copied one per lane with branch-free tiers, the few that depend on output of the same window
-//    are retired in order (whole warp, one byte per lane).  ~14 tokens retire per iteration.
+//  * BLOCK PATH (lz_block): 1 KB of compressed input is staged in shared memory; every lane finds the
+//    token chain through its own 32-byte segment (exit table computed right to left, entries resolved
+//    across lanes), the ~350-500 tokens of the block are listed in stream order and executed 32 per
+//    step, one token per lane: literals from the staged block, matches in dependency rounds.
 //  * The most recent 4 KB of output live in a per-warp shared-memory ring (explicit 32-bit shared
 //    addressing), so match sources are read at shared-memory latency; completed 512-byte blocks are
 //    flushed to HBM with 16-byte aligned vector stores (full-line writes, DRAM traffic == algorithmic
@@ -18,10 +15,11 @@
 //    parsed once by the whole warp; up to 192 bytes they are executed inside the ring, longer runs go
 //    straight to global memory as 16-byte vectors (periodic runs are built in registers, no
 //    store->load round trip) and the ring restarts empty behind them.
-//  * Chunks that compressed >= 4x never enter this machinery: the callers (lz4.cu / snappy.cu) decode
-//    them with the direct global-memory token loop, and hand dense chunks out first (two-pass ticket).
+//  * Chunks that compressed >= 4x never enter this machinery: the callers (lz4_decode.cuh /
+//    snappy_decode.cuh) decode them with the direct global-memory token loop, and the kernels hand
+//    dense chunks out first (two-pass ticket).
 //
-// Format specifics (token grammar, stream end, size limits) come from a Parse policy.
+// Format specifics (token grammar, stream end, size limits) come from a policy.
 #pragma once
 
 #include "common.cuh"
@@ -31,9 +29,8 @@ namespace b200 {
 constexpr uint32_t kRingBytes = 4096;
 constexpr uint32_t kRingMask = kRingBytes - 1;
 constexpr uint32_t kFlushBlock = 512;
-constexpr int kParRounds = 3;          // parallel match rounds per window before in-order retirement
 // A match source is served from the ring only if it is younger than this many bytes
-// (ring size minus the largest output one fast iteration can append, minus alignment slack).
+// (ring size minus the largest output one execution step can append, minus alignment slack).
 constexpr uint32_t kRingReach = kRingBytes - 1024 - 16;
 
 struct LzState {
@@ -52,32 +49,8 @@ struct LzState {
 __device__ __forceinline__ uint32_t ring_idx(const LzState& s, uint32_t off) {
   return (off + s.align) & kRingMask;
 }
-// explicit shared-space accesses on 32-bit addresses (the generic-pointer form costs 64-bit address
-// arithmetic and generic LD/ST on every byte)
-template <int O = 0>
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(O) : "memory");
-  return v;
-}
-template <int O = 0>
-__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u8 [%0+%1], %2;" :: "r"(a), "n"(O), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
-  return r;
-}
 __device__ __forceinline__ uint32_t ring_ld(const LzState& s, uint32_t off) { return lds_u8(s.ring + ring_idx(s, off)); }
 __device__ __forceinline__ void ring_st(const LzState& s, uint32_t off, uint32_t v) { sts_u8(s.ring + ring_idx(s, off), v); }
-template <int O>
-__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.u8 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(O) : "memory");
-  return v;
-}
-
 // Write ring bytes [s.flushed, upto) to global memory.  Vector stores where the global
 // address is 16-byte aligned, byte stores for ragged ends.
 __device__ __forceinline__ void lz_flush(LzState& s, uint32_t upto, int lane) {
@@ -108,224 +81,305 @@ __device__ __forceinline__ void lz_flush_blocks(LzState& s, int lane) {
 }
 
 // ---------------------------------------------------------------------------
-// Parse policies.  parse(b0, p, lane) classifies the byte at window position `lane`
-// as a token start: literal length L, match length M, bytes to the next token, where
-// the 2-byte offset sits (rel. to the token) and whether the token needs the slow path.
+// Format policies.  A "token" is one LZ4 sequence (literals + match) or one Snappy element (literal
+// OR copy).  Everything the block parser needs is a pure function of the token's first byte:
+//   tok_size(b): bytes from this token to the next one (<= kSegBytes), kTokStop for a token the
+//                lane-parallel path does not take (length-extension bytes, long literals, copy-4)
+//   tok_out(b):  output bytes the token produces
+// fields() extracts literal length / match length / offset for execution.
 // ---------------------------------------------------------------------------
-struct Tok {
-  uint32_t L, M, size, off_at;   // off_at: offset field position relative to token start (0 = none)
-  bool stop;
-  uint32_t kind;                 // format-private
-};
+constexpr uint32_t kTokStop = 64;
+
+// 4 bytes at an arbitrary position of a shared-memory buffer (two aligned words + funnel shift)
+__device__ __forceinline__ uint32_t lds_u32_any(uint32_t base, uint32_t pos) {
+  const uint32_t a = base + (pos & ~3u);
+  return __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (pos & 3u) * 8u);
+}
 
 struct Lz4Policy {
-  static constexpr uint32_t kLook = 80;        // fast path needs ip + kLook <= in_n
-  static constexpr uint32_t kMaxFastM = 18;
-  __device__ static __forceinline__ Tok parse(uint32_t b0) {
-    Tok t;
-    t.L = b0 >> 4;
-    const uint32_t mn = b0 & 15u;
-    t.M = mn + 4;
-    t.stop = (t.L == 15u) | (mn == 15u);
-    t.size = 3 + t.L;
-    t.off_at = 1 + t.L;
-    t.kind = 0;
-    return t;
+  __device__ static __forceinline__ uint32_t tok_size(uint32_t b) {
+    const uint32_t L = b >> 4;
+    return (L == 15u || (b & 15u) == 15u) ? kTokStop : 3u + L;
   }
-  __device__ static __forceinline__ uint32_t offset(const uint8_t* __restrict__ p, const Tok& t) {
-    return load_u16(p + t.off_at);
+  __device__ static __forceinline__ uint32_t tok_out(uint32_t b) { return (b >> 4) + (b & 15u) + 4u; }
+  // blk: shared address of the staged block, pos: position of the token in it
+  __device__ static __forceinline__ void fields(uint32_t blk, uint32_t pos, uint32_t& L, uint32_t& M,
+                                                uint32_t& off, uint32_t& lit_at) {
+    const uint32_t x = lds_u32_any(blk, pos);
+    L = (x >> 4) & 15u;
+    M = (x & 15u) + 4u;
+    lit_at = pos + 1u;
+    off = (x >> 8) & 0xffffu;
+    if (L) off = lds_u32_any(blk, pos + 1u + L) & 0xffffu;
   }
-  // does the token starting with byte b0 need the medium / long path?
-  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return (b0 >> 4) == 15u || (b0 & 15u) == 15u; }
+  // does the token starting with byte b0 need the serial path?
+  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return tok_size(b0) == kTokStop; }
 };
 
 struct SnappyPolicy {
-  static constexpr uint32_t kLook = 96;
-  static constexpr uint32_t kMaxFastM = 18;
-  __device__ static __forceinline__ Tok parse(uint32_t b0) {
-    Tok t;
-    const uint32_t kind = b0 & 3u, hi = b0 >> 2;
-    t.kind = kind;
-    t.L = 0; t.M = 0; t.off_at = 1; t.stop = false;
-    if (kind == 0) {
-      t.L = hi + 1; t.size = 1 + t.L; t.off_at = 0;
-      t.stop = t.L > 28u;
-    } else if (kind == 1) {
-      t.M = 4 + (hi & 7u); t.size = 2;
-    } else if (kind == 2) {
-      t.M = hi + 1; t.size = 3;
-      t.stop = t.M > kMaxFastM;
-    } else {
-      t.size = 5; t.stop = true;
-    }
-    return t;
+  __device__ static __forceinline__ uint32_t tok_size(uint32_t b) {
+    const uint32_t kind = b & 3u, h = b >> 2;
+    if (kind == 0u) return h < 31u ? h + 2u : kTokStop;      // literal of h+1 <= 31 bytes
+    return kind == 3u ? kTokStop : kind + 1u;                // copy-1: 2 bytes, copy-2: 3 bytes
   }
-  __device__ static __forceinline__ uint32_t offset(const uint8_t* __restrict__ p, const Tok& t) {
-    if (t.kind == 1) return ((uint32_t)(p[0] >> 5) << 8) | p[1];
-    return load_u16(p + 1);
+  __device__ static __forceinline__ uint32_t tok_out(uint32_t b) {
+    const uint32_t kind = b & 3u, h = b >> 2;
+    return kind == 1u ? 4u + (h & 7u) : h + 1u;
   }
-  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return parse(b0).stop; }
+  __device__ static __forceinline__ void fields(uint32_t blk, uint32_t pos, uint32_t& L, uint32_t& M,
+                                                uint32_t& off, uint32_t& lit_at) {
+    const uint32_t x = lds_u32_any(blk, pos);
+    const uint32_t kind = x & 3u, h = (x >> 2) & 63u;
+    lit_at = pos + 1u;
+    L = kind == 0u ? h + 1u : 0u;
+    M = kind == 0u ? 0u : (kind == 1u ? 4u + (h & 7u) : h + 1u);
+    off = kind == 1u ? (((x >> 5) & 7u) << 8) | ((x >> 8) & 255u) : (x >> 8) & 0xffffu;
+  }
+  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return tok_size(b0) == kTokStop; }
 };
 
-// One fast-path iteration.  Returns number of tokens retired (0: the token at s.ip needs
-// the slow path), or -1 on a malformed stream.
-template <class P>
-__device__ __forceinline__ int lz_fast_iter(LzState& s, int lane) {
-  const uint8_t* __restrict__ win = s.in + s.ip;
-  const uint32_t b0 = win[lane];
-  const Tok t = P::parse(b0);
-  // --- token chain by pointer doubling -------------------------------------------------
-  const unsigned stopmask = __ballot_sync(kFull, t.stop);
-  const uint32_t nxt0 = t.stop ? 64u : (uint32_t)lane + t.size;    // >= 32: leaves the window
-  uint32_t nxt = nxt0;
-  unsigned reach = 1u;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool mine = (reach >> lane) & 1u;
-    const unsigned contrib = (mine && nxt < 32u) ? (1u << nxt) : 0u;
-    reach |= __reduce_or_sync(kFull, contrib);
-    const uint32_t hop = __shfl_sync(kFull, nxt, nxt & 31u);
-    nxt = (nxt < 32u) ? hop : nxt;
-  }
-  const unsigned tokmask = reach & ~stopmask;
-  if (tokmask == 0) return 0;
-  const unsigned hitstop = reach & stopmask;
-  const int last = 31 - __clz(tokmask);
-  const uint32_t adv = hitstop ? (uint32_t)(__ffs(hitstop) - 1) : __shfl_sync(kFull, nxt0, last);
-  const bool is_tok = (tokmask >> lane) & 1u;
+// ---------------------------------------------------------------------------
+// Block path.  One call parses up to kBlkBytes of compressed input and executes its tokens.
+//
+//   1. stage   lane l loads its 32-byte segment of the block (16-byte aligned base) and stores it to
+//              shared memory; kBlkPad more bytes cover tokens that start in the last segment.
+//   2. chain   every lane computes, right to left over its own 32 bytes (held in registers, fully
+//              unrolled), where a token chain entering its segment at byte p leaves it: a 32-entry
+//              exit table per lane.  The true entry of every segment then follows by walking the 32
+//              tables from the known entry of segment 0.  No speculation, no retries.
+//   3. walk    each lane walks the tokens of its segment twice: count them / sum their output
+//              lengths, and after one warp scan write one record per token (block position | output
+//              position) in stream order.
+//   4. execute 32 consecutive tokens per step, one per lane: literals, then matches in dependency
+//              rounds: a match runs as soon as the tokens of this step that produce its source bytes
+//              have run (sources below the step are final).
+// ---------------------------------------------------------------------------
+constexpr uint32_t kSegBytes = 32;
+constexpr uint32_t kBlkBytes = 32 * kSegBytes;
+constexpr uint32_t kBlkPad = 32;
+constexpr uint32_t kBlkStage = kBlkBytes + kBlkPad;
+constexpr uint32_t kMaxStepOut = 1024;              // output bytes one step may append (ring reach depends on it)
+constexpr uint32_t kSmemIn = kRingBytes;            // staged block
+constexpr uint32_t kSmemRec = kSmemIn + kBlkStage;  // token records (4 B each); the exit tables alias them
+constexpr uint32_t kRecBytes = 4 * (kBlkBytes / 2); // a token is at least 2 bytes
+constexpr uint32_t kLzWarpSmem = kSmemRec + kRecBytes;
+static_assert(kRingReach + kMaxStepOut + 16 <= kRingBytes, "ring reach");
+static_assert(kSmemRec % 16 == 0, "record alignment");
 
-  // --- per-token fields, output positions ------------------------------------------------
-  uint32_t off = 0;
-  if (is_tok && t.M) off = P::offset(win + lane, t);
-  const uint32_t len = is_tok ? (t.L + t.M) : 0u;
-  uint32_t incl = len;
+// Returns the number of tokens retired (0: nothing done, the caller takes the serial path), -1 on a
+// malformed stream.
+template <class P>
+__device__ __forceinline__ int lz_block(LzState& s, int lane) {
+  const uint32_t ul = (uint32_t)lane;
+  const uint8_t* const ipp = s.in + s.ip;
+  const uint32_t mis = (uint32_t)((uintptr_t)ipp & 15u);
+  const uint32_t avail = s.in_n - s.ip + mis;                 // bytes from the aligned base to the stream end
+  if (avail < kSegBytes + kBlkPad) return 0;
+  uint32_t nl = (avail - kBlkPad) / kSegBytes;                // segments that lie (with the pad) inside the stream
+  if (nl > 32u) nl = 32u;
+  const uint8_t* const abase = ipp - mis;
+  const uint32_t blk = s.ring + kSmemIn, rec = s.ring + kSmemRec;
+
+  // ---- 1. stage ------------------------------------------------------------------------------
+  uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+  if (ul < nl) {
+    a0 = ld_nc_v4((const uint4*)(abase + kSegBytes * ul));
+    a1 = ld_nc_v4((const uint4*)(abase + kSegBytes * ul + 16u));
+    sts_v4(blk + kSegBytes * ul, a0);
+    sts_v4(blk + kSegBytes * ul + 16u, a1);
+  }
+  if (ul < kBlkPad / 16u) {
+    const uint4 pad = ld_nc_v4((const uint4*)(abase + kSegBytes * nl + 16u * ul));
+    sts_v4(blk + kSegBytes * nl + 16u * ul, pad);
+  }
+  // ---- 2. chain: exit table of this lane's segment ---------------------------------------------
+  {
+    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const uint32_t ex = rec + kSegBytes * ul;
+#pragma unroll
+    for (int p = 31; p >= 0; --p) {
+      const uint32_t b = (w[p >> 2] >> (8 * (p & 3))) & 255u;
+      const uint32_t sz = P::tok_size(b);
+      const uint32_t q = (uint32_t)p + sz;
+      uint32_t code;
+      if (q >= kSegBytes) code = (sz == kTokStop) ? 0xffu : q - kSegBytes;
+      else code = lds_u8(ex + q);
+      sts_u8(ex + (uint32_t)p, code);
+    }
+  }
+  __syncwarp();
+  // entry of every segment: walk the tables from the known entry of segment 0 (warp-uniform)
+  uint32_t e = mis, my_e = 0, stop_lane = 32u;
+  for (uint32_t l = 0; l < nl; ++l) {
+    if (ul == l) my_e = e;
+    const uint32_t x = lds_u8(rec + kSegBytes * l + e);
+    if (x == 0xffu) { stop_lane = l; break; }
+    e = x;
+  }
+  // ---- 3. walk: token count / output bytes of this lane's segment -------------------------------
+  const bool active = ul < nl && ul <= stop_lane;
+  uint32_t p = my_e, cnt = 0, osum = 0;
+  if (active) {
+    while (p < kSegBytes) {
+      const uint32_t b = lds_u8(blk + kSegBytes * ul + p);
+      const uint32_t sz = P::tok_size(b);
+      if (sz == kTokStop) break;
+      ++cnt;
+      osum += P::tok_out(b);
+      p += sz;
+    }
+  }
+  // block end: the stop token, or where the chain leaves the last segment
+  const uint32_t end_pos = stop_lane < 32u ? __shfl_sync(kFull, kSegBytes * ul + p, (int)stop_lane)
+                                           : kSegBytes * nl + e;
+  uint32_t incl = cnt | (osum << 10);                           // cnt <= 16 per lane, osum <= 16 * 64
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t o = __shfl_up_sync(kFull, incl, d);
     if (lane >= d) incl += o;
   }
-  const uint32_t total = __shfl_sync(kFull, incl, 31);
-  if ((uint64_t)s.op + total > s.out_cap) return 0;        // let the slow path find the exact error
-  // From here on output positions are kept in "aligned space" (offset + s.align): the ring index
-  // is then just (pos & mask) and (s.out - s.align)[pos] is the global address.
+  const uint32_t tot = __shfl_sync(kFull, incl, 31);
+  const uint32_t N = tot & 1023u, total_out = tot >> 10;
+  if (N == 0u) return 0;
+  if ((uint64_t)s.op + total_out > s.out_cap) return 0;         // the serial path finds the exact error
+  __syncwarp();                                                 // exit tables are dead: records overwrite them
+  {
+    uint32_t t = (incl & 1023u) - cnt, run = (incl >> 10) - osum, q = my_e;
+    for (uint32_t j = 0; j < cnt; ++j) {
+      const uint32_t b = lds_u8(blk + kSegBytes * ul + q);
+      sts_u32(rec + 4u * t, (kSegBytes * ul + q) | (run << 10));
+      run += P::tok_out(b);
+      q += P::tok_size(b);
+      ++t;
+    }
+  }
+  __syncwarp();
+
+  // ---- 4. execute ------------------------------------------------------------------------------
+  // Output positions are kept in "aligned space" (offset + s.align): the ring index is (pos & mask)
+  // and (s.out - s.align)[pos] is the global address.
   const uint32_t rbase = s.ring;
   const uint8_t* const outa = s.out - s.align;
-  const uint32_t o_lit = s.op + s.align + incl - len;
-  const uint32_t o_mat = o_lit + t.L;
-  const bool bad = is_tok && t.M && (off == 0u || off > o_mat - s.align);
-  if (__any_sync(kFull, bad)) return -1;
-
-  // --- literals: every window byte finds its token and scatters itself --------------------
-  {
-    const unsigned below = reach & (0xffffffffu >> (31 - lane));   // reach bits <= lane (bit 0 always set)
-    const int tk = 31 - __clz(below);
-    const uint32_t tL = __shfl_sync(kFull, t.L, tk);
-    const uint32_t tO = __shfl_sync(kFull, o_lit, tk);
-    const bool tok_ok = (tokmask >> tk) & 1u;
-    const uint32_t k = (uint32_t)lane - (uint32_t)tk - 1u;          // literal index within token tk
-    if (tok_ok && lane > tk && k < tL) sts_u8(rbase + ((tO + k) & kRingMask), b0);
-    // literal bytes past the window can only belong to the last token
-    const uint32_t lL = __shfl_sync(kFull, t.L, last);
-    const uint32_t lO = __shfl_sync(kFull, o_lit, last);
-    if ((uint32_t)last + 1u + lL > 32u) {
-      const uint32_t k2 = 32u + (uint32_t)lane - (uint32_t)last - 1u;
-      if (k2 < lL) sts_u8(rbase + ((lO + k2) & kRingMask), win[32 + lane]);
-    }
-  }
-  // --- matches -------------------------------------------------------------------------------
-  // Round 1 copies, one match per lane, every match whose source bytes are already final
-  // (they end at or below the output position of the first match of the window): on tabular
-  // data that is the majority.  The common case (no overlap, source entirely in the ring or
-  // entirely in flushed global memory, no ring wrap-around) is a branch-free unrolled copy in
-  // tiers with immediate offsets.  The remaining matches depend on output of this same window
-  // and are retired in order, the whole warp copying one match (<= 18 bytes, one byte per
-  // lane) per step.
-  const uint32_t ring_from = max(s.ring_lo, s.op > kRingReach ? s.op - kRingReach : 0u) + s.align;
-  const bool has_match = is_tok && t.M != 0u;
-  unsigned pending = __ballot_sync(kFull, has_match);
-  const uint32_t src0 = o_mat - off;
-  const uint32_t pack = off | (t.M << 16);
-  if (pending) {
-    const uint32_t src_end = src0 + min(t.M, off);           // exclusive end of the bytes this match reads
-    const uint32_t didx = o_mat & kRingMask, sidx = src0 & kRingMask;
-    const bool in_ring = src0 >= ring_from && sidx <= kRingBytes - 20u;
-    const bool far = src0 + t.M <= ring_from;                // flushed long ago: read from global
-    const bool simple = has_match && off >= t.M && didx <= kRingBytes - 20u && (in_ring || far);
-    const uint32_t dp = rbase + didx, sp = rbase + sidx;
-    const uint8_t* const gp = outa + src0;
-    // up to kParRounds parallel rounds: each takes every pending match whose source ends at or below
-    // the output position of the first pending match (everything below it is final)
-    for (int rnd = 0; rnd < kParRounds && pending; ++rnd) {
+  const uint32_t out0 = s.op + s.align;
+  uint32_t t0 = 0;
+  while (t0 < N) {
+    const uint32_t t = t0 + ul;
+    bool valid = t < N;
+    const uint32_t r = lds_u32(rec + 4u * (valid ? t : t0));
+    const uint32_t pos = r & 1023u;
+    const uint32_t dst = out0 + (r >> 10);
+    uint32_t L, M, off, lit_at;
+    P::fields(blk, pos, L, M, off, lit_at);
+    const uint32_t step_lo = __shfl_sync(kFull, dst, 0);
+    // tokens of this step: the leading run that ends within kMaxStepOut bytes (never empty)
+    const unsigned fitm = __ballot_sync(kFull, valid && dst + L + M - step_lo <= kMaxStepOut);
+    const uint32_t n = fitm == kFull ? 32u : (uint32_t)__ffs((int)~fitm) - 1u;
+    valid = ul < n;
+    if (!valid) { L = 0; M = 0; }
+    const uint32_t step_hi = __shfl_sync(kFull, dst + L + M, (int)n - 1);
+    const uint32_t o_mat = dst + L;
+    const bool has = M != 0u;
+    if (__any_sync(kFull, has && (off == 0u || off > o_mat - s.align))) return -1;
+    // literals: straight from the staged block
+    for (uint32_t j = 0; __any_sync(kFull, j < L); ++j)
+      if (j < L) sts_u8(rbase + ((dst + j) & kRingMask), lds_u8(blk + lit_at + j));
     __syncwarp();
-    const int first0 = __ffs(pending) - 1;
-    const uint32_t w = __shfl_sync(kFull, o_mat, first0);
-    const bool ready = ((pending >> lane) & 1u) && (src_end <= w);
-    const bool fast = ready && simple;
-    const bool fast_r = fast && !far, fast_g = fast && far;
-    const unsigned fmask = __ballot_sync(kFull, fast);
-    if (fmask == 0u) break;                                  // first pending match needs the generic path
-#define B200_TIER4(LD, SRC, A, B, C, D)                                                        \
-    {                                                                                          \
-      const uint32_t x0 = LD<A>(SRC), x1 = LD<B>(SRC), x2 = LD<C>(SRC), x3 = LD<D>(SRC);       \
-      sts_u8<A>(dp, x0);                                                                       \
-      if (t.M > B) sts_u8<B>(dp, x1);                                                          \
-      if (t.M > C) sts_u8<C>(dp, x2);                                                          \
-      if (t.M > D) sts_u8<D>(dp, x3);                                                          \
-    }
-#define B200_TAIL10(LD, SRC)                                                                   \
-    {                                                                                          \
-      if (8 < t.M) sts_u8<8>(dp, LD<8>(SRC));    if (9 < t.M) sts_u8<9>(dp, LD<9>(SRC));       \
-      if (10 < t.M) sts_u8<10>(dp, LD<10>(SRC)); if (11 < t.M) sts_u8<11>(dp, LD<11>(SRC));    \
-      if (12 < t.M) sts_u8<12>(dp, LD<12>(SRC)); if (13 < t.M) sts_u8<13>(dp, LD<13>(SRC));    \
-      if (14 < t.M) sts_u8<14>(dp, LD<14>(SRC)); if (15 < t.M) sts_u8<15>(dp, LD<15>(SRC));    \
-      if (16 < t.M) sts_u8<16>(dp, LD<16>(SRC)); if (17 < t.M) sts_u8<17>(dp, LD<17>(SRC));    \
-    }
-    if (fast_r) B200_TIER4(lds_u8, sp, 0, 1, 2, 3)
-    if (__any_sync(kFull, fast_r && t.M > 4u)) {
-      if (fast_r && t.M > 4u) B200_TIER4(lds_u8, sp, 4, 5, 6, 7)
-      if (__any_sync(kFull, fast_r && t.M > 8u)) {
-        if (fast_r && t.M > 8u) B200_TAIL10(lds_u8, sp)
-      }
-    }
-    if (__any_sync(kFull, fast_g)) {
-      // sources flushed long ago (read from global memory), same tiers
-      if (fast_g) B200_TIER4(ldg_u8, gp, 0, 1, 2, 3)
-      if (__any_sync(kFull, fast_g && t.M > 4u)) {
-        if (fast_g && t.M > 4u) B200_TIER4(ldg_u8, gp, 4, 5, 6, 7)
-        if (__any_sync(kFull, fast_g && t.M > 8u)) {
-          if (fast_g && t.M > 8u) B200_TAIL10(ldg_u8, gp)
+    // matches
+    const unsigned hasm = __ballot_sync(kFull, has);
+    if (hasm) {
+      const uint32_t cur_op = step_lo - s.align;
+      const uint32_t ring_from = max(s.ring_lo, cur_op > kRingReach ? cur_op - kRingReach : 0u) + s.align;
+      const uint32_t src = o_mat - off;
+      const uint32_t src_end = src + min(M, off);              // exclusive end of the bytes this match reads
+      // which tokens of this step produce my source bytes?  Token ranges are consecutive, so the
+      // producers are the lanes from the one holding byte max(src, step_lo) to the one holding src_end-1.
+      unsigned dep = 0;
+      const bool inwin = has && src_end > step_lo;
+      if (__any_sync(kFull, inwin)) {
+        const uint32_t key = valid ? dst : 0xffffffffu;
+        const uint32_t qa = max(src, step_lo), qb = src_end - 1u;
+        uint32_t ja = 0, jb = 0;
+#pragma unroll
+        for (uint32_t st = 16; st; st >>= 1) {
+          const uint32_t va = __shfl_sync(kFull, key, (int)(ja + st));
+          const uint32_t vb = __shfl_sync(kFull, key, (int)(jb + st));
+          if (va <= qa) ja += st;
+          if (vb <= qb) jb += st;
         }
+        // own literals precede the own match in program order: drop the self bit
+        if (inwin) dep = ((2u << jb) - 1u) & ~((1u << ja) - 1u) & ~(1u << ul);
       }
-    }
-    pending &= ~fmask;
-    }
-#undef B200_TIER4
-#undef B200_TAIL10
-    // in-order retirement of everything else
-    while (pending) {
-      __syncwarp();
-      const int f = __ffs(pending) - 1;
-      const uint32_t f_omat = __shfl_sync(kFull, o_mat, f);
-      const uint32_t f_pack = __shfl_sync(kFull, pack, f);
-      const uint32_t f_off = f_pack & 0xffffu, f_M = f_pack >> 16;
-      if ((uint32_t)lane < f_M) {
-        uint32_t r = lane;
-        if (r >= f_off) {                                    // overlapping match replicates its period
-          r -= f_off;
-          if (r >= f_off) { r -= f_off; if (r >= f_off) r %= f_off; }
+      const uint32_t didx = o_mat & kRingMask, sidx = src & kRingMask;
+      const bool in_ring = src >= ring_from && sidx + M + 4u <= kRingBytes;
+      const bool far = src + M <= ring_from;                   // flushed long ago: read from global memory
+      // groups of four bytes are loaded, then stored: needs off >= 4 (a shorter period takes the byte loop)
+      const bool simple = has && off >= 4u && didx + M <= kRingBytes && (in_ring || far);
+      const uint32_t dp = rbase + didx, sp = rbase + sidx;
+      const uint8_t* const gp = outa + src;
+      unsigned done = ~hasm;
+      bool pend = has;
+      while (true) {
+        const bool ready = pend && (dep & ~done) == 0u;
+        const unsigned rm = __ballot_sync(kFull, ready);
+        const bool fr = ready && simple && !far, fg = ready && simple && far, gen = ready && !simple;
+        if (fr) {
+          const uint32_t x0 = lds_u8<0>(sp), x1 = lds_u8<1>(sp), x2 = lds_u8<2>(sp), x3 = lds_u8<3>(sp);
+          sts_u8<0>(dp, x0);
+          if (M > 1u) sts_u8<1>(dp, x1);
+          if (M > 2u) sts_u8<2>(dp, x2);
+          if (M > 3u) sts_u8<3>(dp, x3);
         }
-        const uint32_t q = f_omat - f_off + r;
-        const uint32_t b = (q >= ring_from) ? lds_u8(rbase + (q & kRingMask)) : (uint32_t)outa[q];
-        sts_u8(rbase + ((f_omat + lane) & kRingMask), b);
+        for (uint32_t g = 4; __any_sync(kFull, fr && M > g); g += 4) {
+          if (fr && M > g) {
+            const uint32_t s4 = sp + g, d4 = dp + g;
+            const uint32_t x0 = lds_u8<0>(s4), x1 = lds_u8<1>(s4), x2 = lds_u8<2>(s4), x3 = lds_u8<3>(s4);
+            sts_u8<0>(d4, x0);
+            if (M > g + 1u) sts_u8<1>(d4, x1);
+            if (M > g + 2u) sts_u8<2>(d4, x2);
+            if (M > g + 3u) sts_u8<3>(d4, x3);
+          }
+        }
+        if (__any_sync(kFull, fg)) {
+          for (uint32_t g = 0; __any_sync(kFull, fg && M > g); g += 4) {
+            if (fg && M > g) {
+              const uint8_t* const g4 = gp + g;
+              const uint32_t d4 = dp + g;
+              uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+              x0 = ldg_u8<0>(g4);
+              if (M > g + 1u) x1 = ldg_u8<1>(g4);
+              if (M > g + 2u) x2 = ldg_u8<2>(g4);
+              if (M > g + 3u) x3 = ldg_u8<3>(g4);
+              sts_u8<0>(d4, x0);
+              if (M > g + 1u) sts_u8<1>(d4, x1);
+              if (M > g + 2u) sts_u8<2>(d4, x2);
+              if (M > g + 3u) sts_u8<3>(d4, x3);
+            }
+          }
+        }
+        if (__any_sync(kFull, gen)) {
+          // short periods, ring wrap-around, sources straddling the flushed boundary: byte by byte,
+          // in order (a byte may read what this loop wrote off bytes earlier)
+          if (gen) {
+            for (uint32_t j = 0; j < M; ++j) {
+              const uint32_t q = src + j;
+              const uint32_t b = (q >= ring_from) ? lds_u8(rbase + (q & kRingMask)) : (uint32_t)outa[q];
+              sts_u8(rbase + ((o_mat + j) & kRingMask), b);
+            }
+          }
+        }
+        __syncwarp();
+        done |= rm;
+        pend = pend && !ready;
+        if (done == kFull) break;
       }
-      pending &= pending - 1;
     }
+    s.op += step_hi - step_lo;
+    t0 += n;
+    lz_flush_blocks(s, lane);
   }
-  s.op += total;
-  s.ip += adv;
-  return __popc(tokmask);
+  s.ip += end_pos - mis;
+  return (int)N;
 }
-
 
 // ---------------------------------------------------------------------------
 // Medium tokens (too long for the lane-parallel path, L + M <= kMediumMax): executed by the
@@ -451,11 +505,11 @@ __device__ __forceinline__ bool lz_decode_stream(LzState& s, int lane) {
   while (true) {
     if (P::at_end(s)) break;
     // a token that needs the serial path is recognised from its first byte: do not pay for a
-    // speculative window parse that would retire nothing
-    if (s.ip + P::kLook <= s.in_n && !P::is_stop(s.in[s.ip])) {
-      const int r = lz_fast_iter<P>(s, lane);
+    // block parse that would retire nothing
+    if (s.in_n - s.ip >= kSegBytes + kBlkPad && !P::is_stop(s.in[s.ip])) {
+      const int r = lz_block<P>(s, lane);
       if (r < 0) return false;
-      if (r > 0) { lz_flush_blocks(s, lane); continue; }
+      if (r > 0) continue;
     }
     const int r = P::serial_token(s, lane);
     if (r < 0) return false;

@@ -7,199 +7,14 @@
 // elements (reference CHANGELOG.md:182-184).
 #include "common.cuh"
 #include "lz77_compress.cuh"
-#include "lz_decode.cuh"
+#include "snappy_decode.cuh"
 #include "nvcomp/snappy.h"
 
 namespace b200 {
 
-// varint32 preamble; returns false when malformed.  Warp-uniform.
-__device__ __forceinline__ bool snappy_read_preamble(const uint8_t* __restrict__ in, uint32_t in_n,
-                                                     uint32_t& ip, uint64_t& ulen) {
-  ulen = 0;
-  uint32_t shift = 0;
-  while (true) {
-    if (ip >= in_n || shift > 28) return false;
-    const uint32_t b = in[ip++];
-    ulen |= (uint64_t)(b & 0x7fu) << shift;
-    if (!(b & 0x80u)) break;
-    shift += 7;
-  }
-  return ulen <= 0xffffffffull;
-}
-
-__device__ __forceinline__ bool snappy_decode_chunk(const uint8_t* __restrict__ in, uint32_t in_n,
-                                                    uint8_t* out, uint64_t out_cap,
-                                                    uint32_t* produced, int lane) {
-  uint32_t ip = 0;
-  uint64_t ulen;
-  if (!snappy_read_preamble(in, in_n, ip, ulen)) return false;
-  if (ulen > out_cap) return false;
-  const uint32_t n_out = (uint32_t)ulen;
-  uint32_t op = 0;
-  while (ip < in_n) {
-    const uint32_t tag = in[ip++];
-    uint32_t len, off;
-    const uint32_t kind = tag & 3u;
-    if (kind == 0) {
-      len = (tag >> 2) + 1;
-      if (len > 60) {
-        const uint32_t nb = len - 60;
-        if (in_n - ip < nb) return false;
-        uint32_t v = 0;
-        for (uint32_t i = 0; i < nb; ++i) v |= (uint32_t)in[ip + i] << (8 * i);
-        ip += nb;
-        if (v == 0xffffffffu) return false;
-        len = v + 1;
-      }
-      if (len > in_n - ip || len > n_out - op) return false;
-      warp_copy<true>(out + op, in + ip, len, lane);
-      ip += len;
-      op += len;
-      continue;
-    }
-    if (kind == 1) {
-      if (ip >= in_n) return false;
-      len = 4 + ((tag >> 2) & 7u);
-      off = ((tag >> 5) << 8) | in[ip++];
-    } else if (kind == 2) {
-      if (in_n - ip < 2) return false;
-      len = (tag >> 2) + 1;
-      off = load_u16(in + ip);
-      ip += 2;
-      // a run of copy-2 elements with the same offset is one long match (64 bytes per element, so
-      // only a full-length element can have a continuation): lane i inspects element i, the run is
-      // merged and copied once
-      if (len == 64u) {
-        const uint32_t q = ip + 3u * (uint32_t)lane;
-        uint32_t flen = 0;
-        bool same = false;
-        if (q + 3u <= in_n) {
-          const uint32_t t2 = in[q];
-          same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
-          flen = (t2 >> 2) + 1;
-        }
-        const unsigned m = __ballot_sync(kFull, same);
-        const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
-        uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
-        if (len <= n_out - op && add <= n_out - op - len) { len += add; ip += 3u * nf; }
-      }
-    } else {
-      if (in_n - ip < 4) return false;
-      len = (tag >> 2) + 1;
-      off = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8) | ((uint32_t)in[ip + 2] << 16)
-            | ((uint32_t)in[ip + 3] << 24);
-      ip += 4;
-    }
-    if (off == 0 || off > op || len > n_out - op) return false;
-    __syncwarp();
-    warp_match_copy(out + op, off, len, lane);
-    __syncwarp();
-    op += len;
-  }
-  if (op != n_out) return false;
-  *produced = op;
-  return true;
-}
-
-
-// ---------------------------------------------------------------------------
-// v2 decode (lz_decode.cuh): lane-parallel short-element path + this slow path
-// ---------------------------------------------------------------------------
-struct SnappyDecode : SnappyPolicy {
-  __device__ static __forceinline__ bool at_end(const LzState& s) { return s.ip >= s.in_n; }
-  // one element (literal or copy).  A run of copy-2 elements with the same offset -- how Snappy
-  // spells one long match (64 bytes per element) -- is merged and emitted as a single match.
-  __device__ static __forceinline__ int serial_token(LzState& s, int lane) {
-    const uint8_t* __restrict__ in = s.in;
-    const uint32_t in_n = s.in_n;
-    uint32_t ip = s.ip;
-    const uint32_t n_out = (uint32_t)s.out_cap;
-    const uint32_t tag = in[ip++];
-    const uint32_t kind = tag & 3u;
-    uint32_t len, off;
-    if (kind == 0) {
-      len = (tag >> 2) + 1;
-      if (len > 60) {
-        const uint32_t nb = len - 60;
-        if (in_n - ip < nb) return -1;
-        uint32_t v = 0;
-        for (uint32_t i = 0; i < nb; ++i) v |= (uint32_t)in[ip + i] << (8 * i);
-        ip += nb;
-        if (v == 0xffffffffu) return -1;
-        len = v + 1;
-      }
-      if (len > in_n - ip || len > n_out - s.op) return -1;
-      lz_emit_literals(s, in + ip, len, lane);
-      s.ip = ip + len;
-      return 1;
-    }
-    if (kind == 1) {
-      if (ip >= in_n) return -1;
-      len = 4 + ((tag >> 2) & 7u);
-      off = ((tag >> 5) << 8) | in[ip++];
-    } else if (kind == 2) {
-      if (in_n - ip < 2) return -1;
-      len = (tag >> 2) + 1;
-      off = load_u16(in + ip);
-      ip += 2;
-      // merge following copy-2 elements with the same offset (lane i inspects element i); only a
-      // full-length element can have a continuation
-      if (len == 64u) {
-        const uint32_t q = ip + 3u * (uint32_t)lane;
-        uint32_t flen = 0;
-        bool same = false;
-        if (q + 3u <= in_n) {
-          const uint32_t t2 = in[q];
-          same = ((t2 & 3u) == 2u) && (load_u16(in + q + 1) == off);
-          flen = (t2 >> 2) + 1;
-        }
-        const unsigned m = __ballot_sync(kFull, same);
-        const uint32_t nf = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
-        uint32_t add = ((uint32_t)lane < nf) ? flen : 0u;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
-        if (add <= n_out - s.op - min(len, n_out - s.op)) { len += add; ip += 3u * nf; }
-      }
-    } else {
-      if (in_n - ip < 4) return -1;
-      len = (tag >> 2) + 1;
-      off = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8) | ((uint32_t)in[ip + 2] << 16)
-            | ((uint32_t)in[ip + 3] << 24);
-      ip += 4;
-    }
-    if (off == 0 || off > s.op || len > n_out - s.op) return -1;
-    lz_emit_match(s, off, len, lane);
-    s.ip = ip;
-    return 1;
-  }
-};
-
-__device__ __forceinline__ bool snappy_decode_chunk_v2(const uint8_t* in, uint32_t in_n, uint8_t* out,
-                                                       uint64_t out_cap, uint32_t* produced,
-                                                       uint8_t* ring, int lane) {
-  uint32_t ip = 0;
-  uint64_t ulen;
-  if (!snappy_read_preamble(in, in_n, ip, ulen)) return false;
-  if (ulen > out_cap) return false;
-  // Adaptive strategy (see lz4.cu): chunks that compressed >= 4x are long-match dominated and
-  // take the direct global-memory token loop.
-  if (ulen >= 4ull * in_n) return snappy_decode_chunk(in, in_n, out, out_cap, produced, lane);
-  LzState s;
-  s.in = in; s.in_n = in_n; s.out = out; s.out_cap = ulen;
-  s.ip = ip; s.op = 0; s.flushed = 0; s.ring_lo = 0;
-  s.align = (uint32_t)((uintptr_t)out & 15u);
-  s.ring = (uint32_t)__cvta_generic_to_shared(ring);
-  if (!lz_decode_stream<SnappyDecode>(s, lane)) return false;
-  if (s.op != (uint32_t)ulen) return false;
-  *produced = s.op;
-  return true;
-}
-
 constexpr int kLzDecWarps = 4;
-// 10 CTAs x 4 warps per SM (48 registers): measured best of 8 / 10 / 12 (profiles/README.md)
-constexpr int kLzDecCtasPerSm = 10;
+// 7 CTAs x 4 warps per SM: shared memory (ring + staged block + token records per warp) sets the limit
+constexpr int kLzDecCtasPerSm = 7;
 
 __global__ void __launch_bounds__(kLzDecWarps * 32, kLzDecCtasPerSm)
 snappy_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
@@ -209,7 +24,7 @@ snappy_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
                             void* const* __restrict__ out_ptrs,
                             nvcompStatus_t* statuses,
                             unsigned long long* ticket) {
-  __shared__ __align__(16) uint8_t s_ring[kLzDecWarps][kRingBytes];
+  __shared__ __align__(16) uint8_t s_ring[kLzDecWarps][kLzWarpSmem];
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
   const size_t warp_global = (size_t)blockIdx.x * kLzDecWarps + w;

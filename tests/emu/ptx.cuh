@@ -1,0 +1,68 @@
+// tests/emu/ptx.cuh -- TEST INFRASTRUCTURE: host stand-ins for nvcomp_b200/csrc/ptx.cuh (same names,
+// same meaning).  tests/emu puts this directory first on the include path, so the codec headers pick
+// these up instead of the inline-PTX versions and run inside the warp emulator (emu_cuda.h) with
+// bounds checks on every shared and vector global access.
+#pragma once
+
+#include "emu_cuda.h"
+
+namespace b200 {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  emu::Warp* w = emu::g_warp;
+  const uint8_t* q = (const uint8_t*)p;
+  if (q < w->smem || q > w->smem + w->smem_bytes) emu::fail("smem_addr of a pointer outside shared memory");
+  return (uint32_t)(q - w->smem);
+}
+
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
+  if ((uintptr_t)p & 15) emu::fail("misaligned ld_nc_v4 %p", (const void*)p);
+  emu::check_global(p, 16, false);
+  uint4 r; memcpy(&r, p, 16); return r;
+}
+__device__ __forceinline__ void st_v4(uint4* p, const uint4& v) {
+  if ((uintptr_t)p & 15) emu::fail("misaligned st_v4 %p", (void*)p);
+  emu::check_global(p, 16, true);
+  memcpy(p, &v, 16);
+}
+__device__ __forceinline__ uint4 ld_v4(const uint4* p) {
+  if ((uintptr_t)p & 15) emu::fail("misaligned ld_v4 %p", (const void*)p);
+  emu::check_global(p, 16, false);
+  uint4 r; memcpy(&r, p, 16); return r;
+}
+
+template <int O = 0>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { return *emu::smem_ptr(a + O, 1); }
+template <int O = 0>
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { *emu::smem_ptr(a + O, 1) = (uint8_t)v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  if (a & 15u) emu::fail("misaligned lds_v4 %u", a);
+  uint4 r; memcpy(&r, emu::smem_ptr(a, 16), 16); return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, const uint4& v) {
+  if (a & 15u) emu::fail("misaligned sts_v4 %u", a);
+  memcpy(emu::smem_ptr(a, 16), &v, 16);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  if (a & 3u) emu::fail("misaligned lds_u32 %u", a);
+  uint32_t r; memcpy(&r, emu::smem_ptr(a, 4), 4); return r;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  if (a & 3u) emu::fail("misaligned sts_u32 %u", a);
+  memcpy(emu::smem_ptr(a, 4), &v, 4);
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  if (a & 1u) emu::fail("misaligned lds_u16 %u", a);
+  uint16_t r; memcpy(&r, emu::smem_ptr(a, 2), 2); return r;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+  if (a & 1u) emu::fail("misaligned sts_u16 %u", a);
+  const uint16_t x = (uint16_t)v; memcpy(emu::smem_ptr(a, 2), &x, 2);
+}
+template <int O>
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
+  emu::check_global(p + O, 1, false);
+  return p[O];
+}
+
+}  // namespace b200

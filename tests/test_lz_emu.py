@@ -1,0 +1,109 @@
+"""CPU: the warp-level LZ4 / Snappy decode logic of nvcomp_b200/csrc (lz_decode.cuh and the format
+headers) executed in the host warp emulator (tests/emu: 32 fibers, rendezvous at every warp intrinsic,
+bounds-checked shared / vector accesses, guard pages around the global buffers).  This is test
+infrastructure -- the product path is the CUDA library; the GPU parity tests (-m gpu) call that through
+the C ABI.  Here the same headers decode liblz4 / pyarrow-snappy / oracle streams and the committed
+golden vectors, and reject malformed streams without touching memory they do not own."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, sample_inputs
+
+INPUTS = sample_inputs()
+MODES = {"adaptive": 0, "direct": 1, "block": 2}
+
+
+class Emu:
+    def __init__(self):
+        path = os.path.join(ROOT, "tests", "emu", "libemu_lz.so")
+        subprocess.run(["make", "-C", ROOT, "tests/emu/libemu_lz.so"], check=True, stdout=subprocess.DEVNULL)
+        self.lib = C.CDLL(path)
+        self.lib.emu_lz_decode.restype = C.c_int
+        self.lib.emu_lz_decode.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                           C.c_uint, C.c_uint, C.c_char_p, C.c_size_t,
+                                           C.POINTER(C.c_ulonglong)]
+        self.syncs = 0
+
+    def decode(self, codec: str, comp: bytes, cap: int, mode="adaptive", in_mis=0, out_mis=0):
+        out = C.create_string_buffer(max(cap, 1))
+        msg = C.create_string_buffer(256)
+        ns = C.c_ulonglong(0)
+        r = self.lib.emu_lz_decode(0 if codec == "lz4" else 1, MODES[mode], comp, len(comp), out, cap,
+                                   in_mis, out_mis, msg, 256, C.byref(ns))
+        self.syncs = ns.value
+        assert r != -2, f"emulator fault: {msg.value.decode()}"
+        return None if r < 0 else out.raw[:r]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emu()
+
+
+def _streams(oracle, liblz4, data):
+    import pyarrow as pa
+    out = [("lz4", "liblz4", liblz4.compress(data)), ("lz4", "lz4hc12", liblz4.compress(data, 12)),
+           ("lz4", "oracle", oracle.compress("lz4", data)), ("snappy", "oracle", oracle.compress("snappy", data))]
+    if len(data):
+        out.append(("snappy", "pyarrow", pa.Codec("snappy").compress(data).to_pybytes()))
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(INPUTS))
+def test_emulated_decoder_matches_cpu_codecs(emu, oracle, liblz4, name):
+    data = INPUTS[name]
+    for codec, producer, comp in _streams(oracle, liblz4, data):
+        for mode in ("adaptive", "block"):
+            got = emu.decode(codec, comp, len(data), mode)
+            assert got == data, (codec, producer, mode, name)
+
+
+@pytest.mark.parametrize("mis", [(1, 0), (0, 1), (5, 7), (15, 9), (8, 8)])
+def test_emulated_decoder_misaligned_buffers(emu, oracle, liblz4, mis):
+    for name in ("price_walk", "text", "sorted_i64", "ragged_40001"):
+        data = INPUTS[name]
+        for codec, producer, comp in _streams(oracle, liblz4, data):
+            got = emu.decode(codec, comp, len(data), "block", in_mis=mis[0], out_mis=mis[1])
+            assert got == data, (codec, producer, name, mis)
+
+
+def test_emulated_decoder_golden_vectors(emu, golden_dir):
+    man = json.load(open(os.path.join(golden_dir, "manifest.json")))
+    for v in man["vectors"]:
+        comp = open(os.path.join(golden_dir, v["comp"]), "rb").read()
+        raw = open(os.path.join(golden_dir, v["raw"]), "rb").read()
+        for mode in ("adaptive", "block"):
+            assert emu.decode(v["codec"], comp, len(raw), mode) == raw, (v, mode)
+
+
+def test_emulated_decoder_rejects_malformed(emu, oracle):
+    rng = np.random.default_rng(5)
+    for codec in ("lz4", "snappy"):
+        for name in ("price_walk", "text"):
+            data = INPUTS[name]
+            good = oracle.compress(codec, data)
+            n = len(data)
+            assert emu.decode(codec, good, n, "block") == data
+            assert emu.decode(codec, good[:-3], n, "block") is None            # truncated
+            assert emu.decode(codec, good, n - 1, "block") is None             # output too small
+            for _ in range(12):                                                # bit flips: same verdict and bytes as the oracle
+                bad = bytearray(good)
+                for _ in range(3):
+                    i = int(rng.integers(0, len(bad)))
+                    bad[i] ^= 1 << int(rng.integers(0, 8))
+                bad = bytes(bad)
+                want = oracle.decompress(codec, bad, n)
+                got = emu.decode(codec, bad, n, "block")
+                if want is None:
+                    assert got is None
+                else:
+                    assert got == want
+        garbage = rng.integers(0, 256, 5000, dtype=np.uint8).tobytes()
+        want = oracle.decompress(codec, garbage, 65536)
+        got = emu.decode(codec, garbage, 65536, "block")
+        assert (got is None) if want is None else (got == want)
