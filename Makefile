@@ -33,7 +33,7 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
 
 $(ORACLE_LIB): $(ORACLE_SRCS) $(wildcard oracle/*.h)
-	gcc -O3 -march=x86-64-v2 -fPIC -shared -Wall -o $@ $(ORACLE_SRCS)
+	gcc -O3 -march=x86-64-v2 -fPIC -shared -Wall -o $@ $(ORACLE_SRCS) -ldl -lpthread
 
 build/tests/hlif_test: tests/cpp/hlif_test.cu $(LIB) $(HDRS)
 	@mkdir -p build/tests

@@ -54,6 +54,11 @@ struct DecompressionConfig
 {
   size_t decomp_data_size;
   uint32_t num_chunks;
+  /* uncompressed bytes per chunk of the buffer this config describes (from its header, validated) */
+  size_t chunk_bytes;
+  /* upper bound of the compressed buffer's size (header total, or the compression config's bound): sizes the
+   * checksum pass over the compressed payload */
+  size_t comp_bytes_bound;
   /* pinned host status of the last decompress() issued with this config (nvcompSuccess,
    * nvcompErrorCannotDecompress or nvcompErrorBadChecksum); valid after a stream sync */
   nvcompStatus_t* get_status() const;

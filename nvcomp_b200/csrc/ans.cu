@@ -160,7 +160,7 @@ ans_decompress_kernel(const void* const* __restrict__ comp_ptrs,
         const uint32_t* seg_off = (const uint32_t*)(in + 16 + 512);
         for (uint32_t sg = w; sg < h.nseg; sg += kAnsWarps) {
           const uint32_t o0 = seg_off[sg], o1 = seg_off[sg + 1];
-          bool sok = (o0 & 3) == 0 && o0 + 128u <= o1 && o1 <= in_bytes;
+          bool sok = (o0 & 3) == 0 && o0 <= o1 && o1 <= in_bytes && o1 - o0 >= 128u;   // no 32-bit wrap
           if (sok) {
             const uint32_t begin = sg * kAnsSeg;
             const uint32_t ns = min(kAnsSeg, h.n - begin);

@@ -9,6 +9,8 @@
 //   u32 magic 'BTC1', u32 algo | type<<8, u32 uncompressed_bytes, u32 nblocks
 //   u16 desc[nblocks] (padded to 8 bytes)
 //   block payloads, 8-byte aligned, in order; a block covers 128 consecutive elements
+//   if uncompressed_bytes is not a multiple of the element size: one more 8-byte word holding the
+//   uncompressed_bytes % size trailing bytes verbatim (zero padded), so any chunk length round-trips
 // algo 0: desc = bits.  payload = u64 first element, then 128*bits bits: zig-zag of the
 //         delta to the previous element of the block (slot 0 holds 0).
 // algo 1: desc = nz | bits<<8.  payload = 128-bit non-zero mask, then nz*bits bits of the
@@ -105,7 +107,7 @@ __device__ __forceinline__ bool btc_read_header(const uint8_t* in, size_t in_byt
   if (w[0] != kBtcMagic) return false;
   h.algo = w[1] & 0xff; h.type = (w[1] >> 8) & 0xff; h.uncompressed = w[2]; h.nblocks = w[3];
   const uint32_t ts = btc_type_size(h.type);
-  if (ts == 0 || h.algo > 1 || (h.uncompressed % ts)) return false;
+  if (ts == 0 || h.algo > 1) return false;
   const uint32_t n = h.uncompressed / ts;
   if (h.nblocks != (n + kBtcBlock - 1) / kBtcBlock) return false;
   if (16ull + 2ull * h.nblocks > in_bytes) return false;
@@ -116,12 +118,14 @@ __device__ __forceinline__ bool btc_read_header(const uint8_t* in, size_t in_byt
 template <class T>
 struct alignas(sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4) BtcQuad { T e[4]; };
 
+// returns false for a malformed block (sparse mask that disagrees with its non-zero count)
 template <int TS>
-__device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const uint8_t* __restrict__ payload,
+__device__ __forceinline__ bool btc_decode_block(int algo, uint32_t desc, const uint8_t* __restrict__ payload,
                                                  typename BtcElem<TS>::T* out, uint32_t n_valid, int lane) {
   using T = typename BtcElem<TS>::T;
   const uint64_t* p64 = (const uint64_t*)payload;
   uint64_t v[4];
+  bool good = true;
   if (algo == 0) {
     const uint32_t bits = desc & 0xffu;
     const uint64_t first = p64[0];
@@ -193,6 +197,8 @@ __device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const 
   } else {
     const uint32_t bits = desc >> 8;
     const uint64_t mlo = p64[0], mhi = p64[1];
+    // the payload holds exactly nz packed values: a mask with more bits set would read past it
+    good = (uint32_t)(__popcll(mlo) + __popcll(mhi)) == (desc & 0xffu);
     // rank of this lane's first element among the non-zeros
     const uint32_t e0 = 4 * lane;
     uint32_t rank;
@@ -201,7 +207,7 @@ __device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const 
     const uint64_t mw = (e0 < 64) ? (mlo >> e0) : (mhi >> (e0 - 64));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if ((mw >> j) & 1ull) { v[j] = bits ? btc_unpack(p64 + 2, rank, bits) : 0ull; ++rank; }
+      if ((mw >> j) & 1ull) { v[j] = (bits && good) ? btc_unpack(p64 + 2, rank, bits) : 0ull; ++rank; }
       else v[j] = 0;
     }
   }
@@ -217,6 +223,7 @@ __device__ __forceinline__ void btc_decode_block(int algo, uint32_t desc, const 
     for (int j = 0; j < 4; ++j)
       if (e + j < n_valid) out[e + j] = q.e[j];
   }
+  return good;
 }
 
 __global__ void __launch_bounds__(kBtcThreads)
@@ -304,16 +311,24 @@ bitcomp_decompress_kernel(const void* const* __restrict__ comp_ptrs,
             const uint32_t nv = min(kBtcBlock, n_elems - e0);
             const uint8_t* payload = pay_base + s_off[b];
             const uint32_t d = s_desc[b];
+            bool bok;
             switch (ts) {
-              case 1: btc_decode_block<1>(h.algo, d, payload, (uint8_t*)out + e0, nv, lane); break;
-              case 2: btc_decode_block<2>(h.algo, d, payload, (uint16_t*)out + e0, nv, lane); break;
-              case 4: btc_decode_block<4>(h.algo, d, payload, (uint32_t*)out + e0, nv, lane); break;
-              default: btc_decode_block<8>(h.algo, d, payload, (uint64_t*)out + e0, nv, lane); break;
+              case 1: bok = btc_decode_block<1>(h.algo, d, payload, (uint8_t*)out + e0, nv, lane); break;
+              case 2: bok = btc_decode_block<2>(h.algo, d, payload, (uint16_t*)out + e0, nv, lane); break;
+              case 4: bok = btc_decode_block<4>(h.algo, d, payload, (uint32_t*)out + e0, nv, lane); break;
+              default: bok = btc_decode_block<8>(h.algo, d, payload, (uint64_t*)out + e0, nv, lane); break;
             }
+            if (!bok && lane == 0) s_fail = 1;
           }
         }
         base_off += total;
         __syncthreads();
+      }
+      // trailing bytes of a chunk whose length is not a multiple of the element size: stored verbatim
+      const uint32_t tail = h.uncompressed - n_elems * ts;
+      if (tail) {
+        if ((uint64_t)base_off + 8u > in_bytes) s_fail = 1;
+        else if (threadIdx.x < tail && !s_fail) out[n_elems * ts + threadIdx.x] = in[base_off + threadIdx.x];
       }
     }
     __syncthreads();
@@ -475,7 +490,7 @@ bitcomp_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* _
     const uint32_t nblocks = (n_elems + kBtcBlock - 1) / kBtcBlock;
     if (threadIdx.x == 0) {
       uint32_t* hw = (uint32_t*)out;
-      hw[0] = kBtcMagic; hw[1] = (uint32_t)algo | ((uint32_t)type << 8); hw[2] = n_elems * ts; hw[3] = nblocks;
+      hw[0] = kBtcMagic; hw[1] = (uint32_t)algo | ((uint32_t)type << 8); hw[2] = n_bytes; hw[3] = nblocks;
     }
     uint16_t* desc = (uint16_t*)(out + 16);
     uint32_t base_off = (16u + 2u * nblocks + 7u) & ~7u;
@@ -521,7 +536,9 @@ bitcomp_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* _
       base_off += total;
       __syncthreads();
     }
-    if (threadIdx.x == 0) out_bytes[c] = base_off;
+    const uint32_t tail = n_bytes - n_elems * ts;
+    if (tail && threadIdx.x < 8) out[base_off + threadIdx.x] = threadIdx.x < tail ? in[n_elems * ts + threadIdx.x] : (uint8_t)0;
+    if (threadIdx.x == 0) out_bytes[c] = base_off + (tail ? 8u : 0u);
     __syncthreads();
   }
 }
@@ -563,7 +580,8 @@ nvcompStatus_t nvcompBatchedBitcompCompressGetMaxOutputChunkSize(
   const size_t n = max_chunk / ts;
   const size_t nblocks = (n + kBtcBlock - 1) / kBtcBlock;
   // header + descriptors + per block: 16 bytes of header/mask + 128 elements at full width
-  *max_compressed_bytes = 16 + ((2 * nblocks + 7) & ~(size_t)7) + nblocks * (16 + kBtcBlock * ts) + 8;
+  // (+ the trailing-bytes word)
+  *max_compressed_bytes = 16 + ((2 * nblocks + 7) & ~(size_t)7) + nblocks * (16 + kBtcBlock * ts) + 16;
   return nvcompSuccess;
 }
 

@@ -13,6 +13,8 @@
 //   u32 uncompressed_bytes, u32 part_bytes, u32 num_parts
 //   u32 part_off[num_parts+1]      byte offsets of each partition payload (8-aligned)
 //   partition payloads
+//   if uncompressed_bytes is not a multiple of the element size: one 8-byte word at part_off[num_parts]
+//   with the trailing uncompressed_bytes % size bytes verbatim (partitions cover the whole elements)
 // Partition payload (independent, opts.chunk_size bytes of input each):
 //   u64 first[num_deltas]          first value removed by delta layer i
 //   stream runs_0 .. runs_{R-1}, stream vals
@@ -325,10 +327,11 @@ __device__ __forceinline__ bool casc_read_header(const uint8_t* in, size_t in_by
   if (h.magic != kCascMagic) return false;
   const uint32_t ts = casc_type_size(h.type);
   if (ts == 0 || h.R > 7 || h.D > 7) return false;
-  if (h.part_bytes == 0 || h.part_bytes > kCascMaxPart || (h.part_bytes % ts)) return false;
-  if ((uint64_t)h.num_parts * h.part_bytes < h.uncompressed) return false;
-  if (h.num_parts && (uint64_t)(h.num_parts - 1) * h.part_bytes >= h.uncompressed) return false;
-  if (h.uncompressed % ts) return false;
+  // the same limits the compressor enforces: the decoder carves 16-byte aligned shared-memory arrays out of it
+  if (h.part_bytes < 512 || h.part_bytes > kCascMaxPart || (h.part_bytes % 8)) return false;
+  const uint32_t whole = h.uncompressed - h.uncompressed % ts;      // bytes of whole elements
+  if ((uint64_t)h.num_parts * h.part_bytes < whole) return false;
+  if (h.num_parts && (uint64_t)(h.num_parts - 1) * h.part_bytes >= whole) return false;
   if (20ull + 4ull * (h.num_parts + 1ull) > in_bytes) return false;
   return true;
 }
@@ -379,8 +382,8 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
           bool pok = (o0 & 7) == 0 && o0 <= o1 && o1 <= in_bytes;
           if (pok) {
             const uint32_t begin = p * h.part_bytes;
-            const uint32_t nbytes = min(h.part_bytes, h.uncompressed - begin);
             const uint32_t ts = casc_type_size(h.type);
+            const uint32_t nbytes = min(h.part_bytes, h.uncompressed - h.uncompressed % ts - begin);
             switch (ts) {
               case 1: pok = casc_decode_part<1>(in + o0, o1 - o0, out + begin, nbytes, h.R, h.D, sm, P, two_bufs, lane); break;
               case 2: pok = casc_decode_part<2>(in + o0, o1 - o0, out + begin, nbytes / 2, h.R, h.D, sm, P, two_bufs, lane); break;
@@ -391,6 +394,13 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
           if (!pok && lane == 0) s_fail = 1;
           __syncwarp();
         }
+      }
+      // trailing bytes of a chunk whose length is not a multiple of the element size
+      const uint32_t tail = h.uncompressed % ts0;
+      if (tail && w == 0) {
+        const uint32_t to = part_off[h.num_parts];
+        if ((uint64_t)to + 8u > in_bytes) { if (lane == 0) s_fail = 1; }
+        else if ((uint32_t)lane < tail) out[h.uncompressed - tail + lane] = in[to + lane];
       }
     }
     __syncthreads();
@@ -564,7 +574,8 @@ cascaded_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* 
     const uint32_t n = (uint32_t)in_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
     __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
-    const uint32_t num_parts = (n + P - 1) / P;
+    const uint32_t tail = n % ts, whole = n - tail;
+    const uint32_t num_parts = (whole + P - 1) / P;
     if (lane == 0) {
       uint32_t* hw = (uint32_t*)out;
       hw[0] = kCascMagic;
@@ -577,7 +588,7 @@ cascaded_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* 
     for (uint32_t p = 0; p < num_parts; ++p) {
       if (lane == 0) part_off[p] = off;
       const uint32_t begin = p * P;
-      const uint32_t nb = min(P, n - begin);
+      const uint32_t nb = min(P, whole - begin);
       uint32_t sz;
       switch (ts) {
         case 1: sz = casc_encode_part<1>(in + begin, nb, opts.num_RLEs, opts.num_deltas, opts.use_bp != 0,
@@ -591,7 +602,8 @@ cascaded_compress_kernel(const void* const* __restrict__ in_ptrs, const size_t* 
       }
       off += (sz + 7u) & ~7u;
     }
-    if (lane == 0) { part_off[num_parts] = off; out_bytes[c] = off; }
+    if (lane == 0) { part_off[num_parts] = off; out_bytes[c] = off + (tail ? 8u : 0u); }
+    if (tail && lane < 8) out[off + lane] = (uint32_t)lane < tail ? in[whole + lane] : (uint8_t)0;
     __syncwarp();
   }
 }
@@ -642,7 +654,7 @@ nvcompStatus_t nvcompBatchedCascadedCompressGetMaxOutputChunkSize(
   if (st != nvcompSuccess) return st;
   if (max_chunk > nvcompCascadedCompressionMaxAllowedChunkSize) return nvcompErrorChunkSizeTooLarge;
   const size_t parts = (max_chunk + opts.chunk_size - 1) / opts.chunk_size;
-  *max_compressed_bytes = ((20 + 4 * (parts + 1) + 7) & ~(size_t)7) + parts * casc_part_bound(opts) + 8;
+  *max_compressed_bytes = ((20 + 4 * (parts + 1) + 7) & ~(size_t)7) + parts * casc_part_bound(opts) + 16;
   return nvcompSuccess;
 }
 
@@ -666,12 +678,8 @@ nvcompStatus_t nvcompBatchedCascadedCompressAsync(
   if (nw > kCascCompWarps) nw = kCascCompWarps;
   if (nw < 1) return nvcompErrorInvalidValue;
   const size_t smem = (size_t)nw * per_warp;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(cascaded_compress_kernel,
-        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  B200_CUDA_TRY(ensure_dynamic_smem(cascaded_compress_kernel, 227 * 1024, smem_set));
   const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
   const int grid = persistent_grid(ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm), batch, nw);
   cascaded_compress_kernel<<<grid, nw * 32, smem, stream>>>(
@@ -713,12 +721,8 @@ nvcompStatus_t nvcompBatchedCascadedDecompressAsync(
     ticket = (unsigned long long*)temp;
     B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(cascaded_decompress_kernel,
-        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCascSmem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  B200_CUDA_TRY(ensure_dynamic_smem(cascaded_decompress_kernel, (int)kCascSmem, smem_set));
   const int grid = persistent_grid(2, batch, 1);
   cascaded_decompress_kernel<<<grid, kCascWarps * 32, kCascSmem, stream>>>(
       comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);

@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <atomic>
+
 #include "nvcomp/shared_types.h"
 #include <ptx.cuh>   // found through -I (csrc/ for the library; tests/emu shadows it for the host emulator)
 
@@ -203,6 +205,21 @@ inline int persistent_grid(int ctas_per_sm, size_t work_items, int work_per_cta)
   size_t cap = (size_t)kNumSMsB200 * (size_t)ctas_per_sm;
   size_t g = need < cap ? need : cap;
   return (int)(g == 0 ? 1 : g);
+}
+
+// Opt-in dynamic shared memory of a kernel.  The attribute is per device (and per context), so the
+// "already set" memo is a per-device bitmask, updated atomically: safe from several host threads and for
+// one process driving several GPUs (reference benchmarks/benchmark_allgather.cpp:359-368 pattern).
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>& memo) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && ((memo.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && tracked) memo.fetch_or(1ull << dev, std::memory_order_release);
+  return e;
 }
 
 // call logging (log.cu): NVCOMP_LOG_LEVEL >= 3 logs every low-level API call

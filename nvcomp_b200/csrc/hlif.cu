@@ -8,16 +8,18 @@
 //               status reduction into pinned host memory (DecompressionConfig::get_status()).
 // Container (8-byte aligned):
 //   HlifHeader (72 B) | u64 chunk_bytes[num_chunks] | chunks (each 8-byte aligned)
-// Checksums (optional, ChecksumPolicy): a 32-bit position-mixed sum of the uncompressed buffer and
-// of the compressed payload -- like the reference's HLIF checksum it is *not* a standard CRC32
-// (doc/highlevel_cpp_quickstart.md:59).
+// Checksums (optional, ChecksumPolicy; reference doc/highlevel_cpp_quickstart.md:59, policies at
+// examples/high_level_quickstart_example.cpp:244-322): CRC-32 (crc32.cu) of the whole uncompressed buffer and
+// of the whole compressed payload -- size table and every chunk, i.e. all bytes after the header.
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstring>
 #include <memory>
 #include <string>
 
 #include "common.cuh"
+#include "crc32.cuh"
 #include "nvcomp/nvcompManagerFactory.hpp"
 
 namespace nvcomp {
@@ -193,24 +195,6 @@ hlif_setup_decompress(const uint8_t* comp_buffer, size_t num_chunks, size_t chun
   }
 }
 
-// position-mixed 32-bit checksum: sum over 4-byte words of (word * (2*index+1)) mod 2^32, atomically folded
-__global__ void hlif_checksum(const uint8_t* data, size_t n, uint32_t* result) {
-  uint32_t acc = 0;
-  const size_t nw = n >> 2;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const bool aligned = (((uintptr_t)data) & 3) == 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += stride) {
-    uint32_t v;
-    if (aligned) v = ((const uint32_t*)data)[i];
-    else v = (uint32_t)data[4 * i] | ((uint32_t)data[4 * i + 1] << 8) | ((uint32_t)data[4 * i + 2] << 16) | ((uint32_t)data[4 * i + 3] << 24);
-    acc += v * (uint32_t)(2 * i + 1);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (size_t i = nw << 2; i < n; ++i) acc += (uint32_t)data[i] * (uint32_t)(2 * i + 7);
-  for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(b200::kFull, acc, d);
-  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(result, acc);
-}
-
 __global__ void hlif_store_checksums(uint8_t* comp_buffer, const uint32_t* sums) {
   HlifHeader* h = (HlifHeader*)comp_buffer;
   h->checksum_uncomp = sums[0];
@@ -242,11 +226,12 @@ struct ManagerImpl {
   bool computes() const { return policy == ComputeAndNoVerify || policy == ComputeAndVerifyIfPresent || policy == ComputeAndVerify; }
   bool verifies() const { return policy == NoComputeAndVerifyIfPresent || policy == ComputeAndVerifyIfPresent || policy == ComputeAndVerify; }
 
-  struct Layout { size_t ptrs, sizes, outptrs, caps, actual, offsets, statuses, sums, temp, temp_bytes, slab, total; };
+  struct Layout { size_t ptrs, sizes, outptrs, caps, actual, offsets, statuses, sums, crc, temp, temp_bytes, slab, total; };
 
   static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
-  Layout compress_layout(size_t n_chunks) const {
+  // crc_bytes: the longest buffer a checksum pass hashes with this layout (0 when no checksums are computed)
+  Layout compress_layout(size_t n_chunks, size_t crc_bytes) const {
     Layout L{};
     size_t max_out = 0, temp = 0;
     check(fmt.comp_max(fmt, chunk, &max_out), "CompressGetMaxOutputChunkSize");
@@ -259,15 +244,16 @@ struct ManagerImpl {
     L.caps = off; off += al(8 * n_chunks);       // compressed sizes
     L.offsets = off; off += al(8 * n_chunks);
     L.sums = off; off += 256;
+    L.crc = off; off += al(4 * b200::crc_scratch_words(crc_bytes));
     L.temp = off; L.temp_bytes = temp; off += al(temp);
     L.slab = off; off += al(max_out * n_chunks);
     L.total = off;
     return L;
   }
-  Layout decompress_layout(size_t n_chunks) const {
+  Layout decompress_layout(size_t n_chunks, size_t chunk_bytes, size_t crc_bytes) const {
     Layout L{};
     size_t temp = 0;
-    check(fmt.decomp_temp(n_chunks, chunk, &temp), "DecompressGetTempSize");
+    check(fmt.decomp_temp(n_chunks, chunk_bytes, &temp), "DecompressGetTempSize");
     size_t off = 0;
     L.ptrs = off; off += al(8 * n_chunks);
     L.sizes = off; off += al(8 * n_chunks);
@@ -276,6 +262,7 @@ struct ManagerImpl {
     L.actual = off; off += al(8 * n_chunks);
     L.statuses = off; off += al(4 * n_chunks);
     L.sums = off; off += 256;
+    L.crc = off; off += al(4 * b200::crc_scratch_words(crc_bytes));
     L.temp = off; L.temp_bytes = temp; off += al(temp);
     L.total = off;
     return L;
@@ -292,6 +279,11 @@ struct ManagerImpl {
   }
 
   size_t n_chunks_of(size_t bytes) const { return bytes == 0 ? 0 : (bytes + chunk - 1) / chunk; }
+  // longest span one checksum pass hashes for an (uncompressed, compressed-bound) pair under this policy
+  size_t crc_span(size_t uncomp, size_t comp_bound) const {
+    if (!computes() && !verifies()) return 0;
+    return uncomp > comp_bound ? uncomp : comp_bound;
+  }
 
   CompressionConfig configure_compression(size_t n) {
     CompressionConfig c;
@@ -301,7 +293,7 @@ struct ManagerImpl {
     check(fmt.comp_max(fmt, chunk, &max_out), "CompressGetMaxOutputChunkSize");
     c.max_compressed_buffer_size = kHeaderBytes + 8 * c.num_chunks + c.num_chunks * ((max_out + 7) & ~(size_t)7) + 8;
     c.status = std::make_shared<StatusHolder>();
-    const Layout L = compress_layout(c.num_chunks ? c.num_chunks : 1);
+    const Layout L = compress_layout(c.num_chunks ? c.num_chunks : 1, crc_span(n, c.max_compressed_buffer_size));
     if (L.total > required_scratch) required_scratch = L.total;
     return c;
   }
@@ -310,7 +302,7 @@ struct ManagerImpl {
     check(cudaSetDevice(device), "cudaSetDevice");
     if (((uintptr_t)out & 7) != 0) throw NVCompException(nvcompErrorAlignment, "compressed buffer must be 8-byte aligned");
     const size_t n = cfg.uncompressed_buffer_size, nc = cfg.num_chunks;
-    const Layout L = compress_layout(nc ? nc : 1);
+    const Layout L = compress_layout(nc ? nc : 1, crc_span(n, cfg.max_compressed_buffer_size));
     ensure_scratch(L.total);
     HlifHeader h{};
     h.magic = kHlifMagic; h.format = fmt.format; std::memcpy(h.opts, fmt.opts, 24);
@@ -332,11 +324,14 @@ struct ManagerImpl {
     hlif_layout<<<1, 1024, 0, stream>>>(csizes, nc, h, out, offsets);
     if (nc) hlif_gather<<<(unsigned)nc, 256, 0, stream>>>(outptrs, csizes, offsets, out);
     if (computes()) {
-      check(cudaMemsetAsync(sums, 0, 8, stream), "memset");
-      hlif_checksum<<<b200::kNumSMsB200 * 4, 256, 0, stream>>>(in, n, sums);
-      // compressed payload checksum covers the size table + chunks (total known only on device: use max span)
-      // -> computed over the table (fixed size) to stay asynchronous
-      hlif_checksum<<<b200::kNumSMsB200, 256, 0, stream>>>(out + kHeaderBytes, 8 * nc, sums + 1);
+      uint32_t* crc_scratch = (uint32_t*)(scratch + L.crc);
+      check(b200::crc32_buffer_async(in, n, nullptr, 0, n, crc_scratch, sums, stream), "uncompressed checksum");
+      // the compressed payload (size table + every chunk) ends at header.total_bytes, which only the device knows:
+      // the pass is sized for the bound and reads the length from the header just written (stays asynchronous)
+      const unsigned long long* total_dev = (const unsigned long long*)(out + offsetof(HlifHeader, total_bytes));
+      check(b200::crc32_buffer_async(out + kHeaderBytes, 0, total_dev, kHeaderBytes,
+                                     cfg.max_compressed_buffer_size - kHeaderBytes, crc_scratch, sums + 1, stream),
+            "compressed checksum");
       hlif_store_checksums<<<1, 1, 0, stream>>>(out, sums);
     }
     if (cfg.status && cfg.status->host) hlif_set_status<<<1, 1, 0, stream>>>(cfg.status->host, nvcompSuccess);
@@ -356,12 +351,21 @@ struct ManagerImpl {
     if (h.format != fmt.format) throw NVCompException(nvcompErrorInvalidValue, "buffer was compressed with another format");
     if (policy == ComputeAndVerify && !(h.flags & 1u))
       throw NVCompException(nvcompErrorCannotVerifyChecksums, "checksums requested but absent from the buffer");
+    // the header is untrusted input: every field the pointer setup uses is checked against the others
+    size_t probe = 0;
+    if (h.chunk_bytes == 0 || fmt.comp_max(fmt, (size_t)h.chunk_bytes, &probe) != nvcompSuccess)
+      throw NVCompException(nvcompErrorInvalidValue, "corrupt header: chunk size");
+    const uint64_t want_chunks = h.uncompressed_bytes == 0 ? 0 : (h.uncompressed_bytes + h.chunk_bytes - 1) / h.chunk_bytes;
+    if ((uint64_t)h.num_chunks != want_chunks || h.total_bytes < kHeaderBytes + 8ull * h.num_chunks)
+      throw NVCompException(nvcompErrorInvalidValue, "corrupt header: chunk count");
     DecompressionConfig d;
     d.decomp_data_size = h.uncompressed_bytes;
     d.num_chunks = h.num_chunks;
+    d.chunk_bytes = (size_t)h.chunk_bytes;
+    d.comp_bytes_bound = (size_t)h.total_bytes;
     d.status = std::make_shared<StatusHolder>();
-    chunk = h.chunk_bytes;
-    const Layout L = decompress_layout(d.num_chunks ? d.num_chunks : 1);
+    const Layout L = decompress_layout(d.num_chunks ? d.num_chunks : 1, d.chunk_bytes,
+                                       crc_span(d.decomp_data_size, d.comp_bytes_bound));
     if (L.total > required_scratch) required_scratch = L.total;
     return d;
   }
@@ -370,6 +374,8 @@ struct ManagerImpl {
     DecompressionConfig d;
     d.decomp_data_size = c.uncompressed_buffer_size;
     d.num_chunks = (uint32_t)c.num_chunks;
+    d.chunk_bytes = chunk;
+    d.comp_bytes_bound = c.max_compressed_buffer_size;
     d.status = std::make_shared<StatusHolder>();
     return d;
   }
@@ -377,7 +383,7 @@ struct ManagerImpl {
   void decompress(uint8_t* out, const uint8_t* comp, const DecompressionConfig& cfg) {
     check(cudaSetDevice(device), "cudaSetDevice");
     const size_t nc = cfg.num_chunks;
-    const Layout L = decompress_layout(nc ? nc : 1);
+    const Layout L = decompress_layout(nc ? nc : 1, cfg.chunk_bytes, crc_span(cfg.decomp_data_size, cfg.comp_bytes_bound));
     ensure_scratch(L.total);
     const void** ptrs = (const void**)(scratch + L.ptrs);
     size_t* sizes = (size_t*)(scratch + L.sizes);
@@ -387,16 +393,20 @@ struct ManagerImpl {
     nvcompStatus_t* statuses = (nvcompStatus_t*)(scratch + L.statuses);
     uint32_t* sums = (uint32_t*)(scratch + L.sums);
     if (nc) {
-      hlif_setup_decompress<<<1, 1024, 0, stream>>>(comp, nc, chunk, cfg.decomp_data_size, out, ptrs, sizes, outptrs, caps);
+      hlif_setup_decompress<<<1, 1024, 0, stream>>>(comp, nc, cfg.chunk_bytes, cfg.decomp_data_size, out, ptrs, sizes, outptrs, caps);
       check(fmt.decomp(ptrs, sizes, caps, actual, nc, scratch + L.temp, L.temp_bytes, outptrs, statuses, stream),
             "DecompressAsync");
     }
     int verify = 0;
     if (verifies()) {
       // verification is decided on the device from the header flag (no host sync here)
-      check(cudaMemsetAsync(sums, 0, 8, stream), "memset");
-      hlif_checksum<<<b200::kNumSMsB200 * 4, 256, 0, stream>>>(out, cfg.decomp_data_size, sums);
-      hlif_checksum<<<b200::kNumSMsB200, 256, 0, stream>>>(comp + kHeaderBytes, 8 * nc, sums + 1);
+      uint32_t* crc_scratch = (uint32_t*)(scratch + L.crc);
+      check(b200::crc32_buffer_async(out, cfg.decomp_data_size, nullptr, 0, cfg.decomp_data_size, crc_scratch, sums, stream),
+            "uncompressed checksum");
+      const unsigned long long* total_dev = (const unsigned long long*)(comp + offsetof(HlifHeader, total_bytes));
+      const size_t bound = cfg.comp_bytes_bound > kHeaderBytes ? cfg.comp_bytes_bound - kHeaderBytes : 0;
+      check(b200::crc32_buffer_async(comp + kHeaderBytes, 0, total_dev, kHeaderBytes, bound, crc_scratch, sums + 1, stream),
+            "compressed checksum");
       verify = 1;
     }
     if (cfg.status && cfg.status->host)

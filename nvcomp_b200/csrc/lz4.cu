@@ -36,8 +36,49 @@ lz4_size_kernel(const void* const* __restrict__ comp_ptrs, const size_t* __restr
 
 
 constexpr int kLzDecWarps = 4;
-// 7 CTAs x 4 warps per SM: shared memory (ring + staged block + token records per warp) sets the limit
+// dense kernel: 7 CTAs x 4 warps per SM -- shared memory (ring + staged block + token records per warp) sets the limit
 constexpr int kLzDecCtasPerSm = 7;
+// light kernel: no shared memory, 10 CTAs x 4 warps per SM (long copies want many warps in flight)
+constexpr int kLzLightCtasPerSm = 10;
+
+// A batch is decoded by two kernels.  "Light" chunks -- compressed >= 4x (long matches, typed run-length data) or
+// practically incompressible (one long literal run) -- are streamed by the direct global-memory sequence loop,
+// which needs no shared memory and runs at high occupancy.  Everything else is dense short-token data and goes
+// to the block-parallel decoder (lz_decode.cuh).  Both kernels walk the whole batch with their own ticket counter
+// and skip the other kernel's chunks.
+__device__ __forceinline__ bool lz_chunk_is_light(uint64_t cap, uint64_t in_n) {
+  return cap >= 4ull * in_n || in_n + (cap >> 6) >= cap;
+}
+
+__global__ void __launch_bounds__(kLzDecWarps * 32, kLzLightCtasPerSm)
+lz4_decompress_light_kernel(const void* const* __restrict__ comp_ptrs,
+                            const size_t* __restrict__ comp_bytes,
+                            const size_t* __restrict__ out_caps,
+                            size_t* actual_bytes, size_t batch,
+                            void* const* __restrict__ out_ptrs,
+                            nvcompStatus_t* statuses,
+                            unsigned long long* ticket) {
+  const int lane = lane_id();
+  const size_t warp_global = (size_t)blockIdx.x * kLzDecWarps + (threadIdx.x >> 5);
+  const size_t warps_total = (size_t)gridDim.x * kLzDecWarps;
+  WarpTicket sched(ticket, warp_global, warps_total);
+  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+    const size_t in_n64 = comp_bytes[c];
+    const uint64_t cap = (uint64_t)out_caps[c];
+    if (!lz_chunk_is_light(cap, in_n64)) continue;
+    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
+    uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
+    uint32_t produced = 0;
+    bool ok = in_n64 <= 0xffffffffull;
+    if (ok) ok = lz4_decode_chunk_direct(in, (uint32_t)in_n64, out, cap, &produced, lane);
+    if (lane == 0) {
+      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
+      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
+    }
+    __syncwarp();
+  }
+}
 
 __global__ void __launch_bounds__(kLzDecWarps * 32, kLzDecCtasPerSm)
 lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
@@ -52,28 +93,22 @@ lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
   const int w = threadIdx.x >> 5;
   const size_t warp_global = (size_t)blockIdx.x * kLzDecWarps + w;
   const size_t warps_total = (size_t)gridDim.x * kLzDecWarps;
-  // Two passes over the ticket space: dense short-token chunks (compressed < 4x, the expensive
-  // ones) are handed out first, cheap long-match chunks fill the tail -- unequal chunks would
-  // otherwise leave a few warps finishing expensive chunks alone at the end of the batch.
-  for (int pass = 0; pass < 2; ++pass) {
-    WarpTicket sched(ticket ? ticket + pass : nullptr, warp_global, warps_total);
-    for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
-      const size_t in_n64 = comp_bytes[c];
-      const uint64_t cap = (uint64_t)out_caps[c];
-      const bool heavy = cap < 4ull * in_n64;
-      if (heavy != (pass == 0)) continue;
-      const uint8_t* in = (const uint8_t*)comp_ptrs[c];
-      uint8_t* out = (uint8_t*)out_ptrs[c];
-      __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
-      uint32_t produced = 0;
-      bool ok = in_n64 <= 0xffffffffull;
-      if (ok) ok = lz4_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane);
-      if (lane == 0) {
-        if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
-        if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
-      }
-      __syncwarp();
+  WarpTicket sched(ticket, warp_global, warps_total);
+  for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
+    const size_t in_n64 = comp_bytes[c];
+    const uint64_t cap = (uint64_t)out_caps[c];
+    if (lz_chunk_is_light(cap, in_n64)) continue;
+    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
+    uint8_t* out = (uint8_t*)out_ptrs[c];
+    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
+    uint32_t produced = 0;
+    bool ok = in_n64 <= 0xffffffffull;
+    if (ok) ok = lz4_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane, false);
+    if (lane == 0) {
+      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
+      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
     }
+    __syncwarp();
   }
 }
 
@@ -191,12 +226,8 @@ nvcompStatus_t nvcompBatchedLZ4CompressAsync(
     B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
   }
   const size_t smem = (size_t)kCompWarpsPerCta * kHashBytesPerWarp;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(lz4_compress_kernel,
-        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  B200_CUDA_TRY(ensure_dynamic_smem(lz4_compress_kernel, (int)smem, smem_set));
   const int grid = persistent_grid(6, batch, kCompWarpsPerCta);
   lz4_compress_kernel<<<grid, kCompWarpsPerCta * 32, smem, stream>>>(
       in_ptrs, in_bytes, batch, out_ptrs, out_bytes, step, ticket);
@@ -240,9 +271,12 @@ nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
     ticket = (unsigned long long*)temp;
     B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned long long), stream));
   }
+  const int grid_l = persistent_grid(kLzLightCtasPerSm, batch, kLzDecWarps);
+  lz4_decompress_light_kernel<<<grid_l, kLzDecWarps * 32, 0, stream>>>(
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
   const int grid = persistent_grid(kLzDecCtasPerSm, batch, kLzDecWarps);
   lz4_decompress_v2_kernel<<<grid, kLzDecWarps * 32, 0, stream>>>(
-      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket ? ticket + 1 : nullptr);
   B200_CUDA_TRY(cudaGetLastError());
   return nvcompSuccess;
 }

@@ -83,26 +83,33 @@ __device__ __forceinline__ void lz_flush_blocks(LzState& s, int lane) {
 // ---------------------------------------------------------------------------
 // Format policies.  A "token" is one LZ4 sequence (literals + match) or one Snappy element (literal
 // OR copy).  Everything the block parser needs is a pure function of the token's first byte:
-//   tok_size(b): bytes from this token to the next one (<= kSegBytes), kTokStop for a token the
-//                lane-parallel path does not take (length-extension bytes, long literals, copy-4)
-//   tok_out(b):  output bytes the token produces
+//   sizes4(w): for the four bytes of w, taken as token tags, the distance to the next token (1..32),
+//              or kTokStop for a token the lane-parallel path does not take (length-extension
+//              bytes, long literals / copies, copy-4) -- SIMD within a 32-bit register
 // fields() extracts literal length / match length / offset for execution.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kTokStop = 64;
+constexpr uint32_t kMaxTokOut = 32;     // output bytes of one fast token (32 tokens x 32 bytes = one step)
 
 // 4 bytes at an arbitrary position of a shared-memory buffer (two aligned words + funnel shift)
 __device__ __forceinline__ uint32_t lds_u32_any(uint32_t base, uint32_t pos) {
   const uint32_t a = base + (pos & ~3u);
   return __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (pos & 3u) * 8u);
 }
+// offset of byte p of a lane's 32-byte row in the lane-private bank layout (word (p >> 2) * 32 + lane)
+__device__ __forceinline__ uint32_t lane_private(uint32_t p) { return (p >> 2) * 124u + p; }
+// per-byte mask 0xff where the low bit of the byte of x is set (x has only bit 0 of every byte)
+__device__ __forceinline__ uint32_t byte_mask(uint32_t x) { return (x << 8) - x; }
 
 struct Lz4Policy {
-  __device__ static __forceinline__ uint32_t tok_size(uint32_t b) {
-    const uint32_t L = b >> 4;
-    return (L == 15u || (b & 15u) == 15u) ? kTokStop : 3u + L;
+  // sequence: token, L literals, 2-byte offset; fast when neither nibble is 15
+  __device__ static __forceinline__ uint32_t sizes4(uint32_t w) {
+    const uint32_t L = (w >> 4) & 0x0f0f0f0fu, Mn = w & 0x0f0f0f0fu;
+    // nibble == 15  <=>  nibble + 1 carries into bit 4
+    const uint32_t stop = (((L + 0x01010101u) | (Mn + 0x01010101u)) >> 4) & 0x01010101u;
+    const uint32_t sm = byte_mask(stop);
+    return ((L + 0x03030303u) & ~sm) | (sm & 0x40404040u);
   }
-  __device__ static __forceinline__ uint32_t tok_out(uint32_t b) { return (b >> 4) + (b & 15u) + 4u; }
-  // blk: shared address of the staged block, pos: position of the token in it
   __device__ static __forceinline__ void fields(uint32_t blk, uint32_t pos, uint32_t& L, uint32_t& M,
                                                 uint32_t& off, uint32_t& lit_at) {
     const uint32_t x = lds_u32_any(blk, pos);
@@ -113,58 +120,70 @@ struct Lz4Policy {
     if (L) off = lds_u32_any(blk, pos + 1u + L) & 0xffffu;
   }
   // does the token starting with byte b0 need the serial path?
-  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return tok_size(b0) == kTokStop; }
+  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return (b0 >> 4) == 15u || (b0 & 15u) == 15u; }
 };
 
 struct SnappyPolicy {
-  __device__ static __forceinline__ uint32_t tok_size(uint32_t b) {
-    const uint32_t kind = b & 3u, h = b >> 2;
-    if (kind == 0u) return h < 31u ? h + 2u : kTokStop;      // literal of h+1 <= 31 bytes
-    return kind == 3u ? kTokStop : kind + 1u;                // copy-1: 2 bytes, copy-2: 3 bytes
-  }
-  __device__ static __forceinline__ uint32_t tok_out(uint32_t b) {
-    const uint32_t kind = b & 3u, h = b >> 2;
-    return kind == 1u ? 4u + (h & 7u) : h + 1u;
+  // literal (kind 0): 1 + (h+1) bytes, fast up to 31 literal bytes; copy-1: 2 bytes; copy-2: 3 bytes, fast up to
+  // kMaxTokOut output bytes; copy-4: serial
+  __device__ static __forceinline__ uint32_t sizes4(uint32_t w) {
+    const uint32_t kind = w & 0x03030303u, h = (w >> 2) & 0x3f3f3f3fu;
+    const uint32_t k1 = kind & 0x01010101u, k2 = (kind >> 1) & 0x01010101u;
+    const uint32_t nz = byte_mask(k1 | k2);                       // 0xff where the element is a copy
+    const uint32_t sz = ((kind + 0x01010101u) & nz) | ((h + 0x02020202u) & ~nz);
+    // stops: kind 3; literal with h >= 31; copy-2 with h >= 32 (more than 32 output bytes)
+    const uint32_t h31 = ((h + 0x61616161u) >> 7) & 0x01010101u;  // h >= 31
+    const uint32_t h32 = (h >> 5) & 0x01010101u;                  // h >= 32
+    const uint32_t stop = (k1 & k2) | (h31 & ~(k1 | k2)) | (h32 & k2);
+    const uint32_t sm = byte_mask(stop);
+    return (sz & ~sm) | (sm & 0x40404040u);
   }
   __device__ static __forceinline__ void fields(uint32_t blk, uint32_t pos, uint32_t& L, uint32_t& M,
                                                 uint32_t& off, uint32_t& lit_at) {
     const uint32_t x = lds_u32_any(blk, pos);
     const uint32_t kind = x & 3u, h = (x >> 2) & 63u;
     lit_at = pos + 1u;
-    L = kind == 0u ? h + 1u : 0u;
-    M = kind == 0u ? 0u : (kind == 1u ? 4u + (h & 7u) : h + 1u);
-    off = kind == 1u ? (((x >> 5) & 7u) << 8) | ((x >> 8) & 255u) : (x >> 8) & 0xffffu;
+    const uint32_t len = kind == 1u ? 4u + (h & 7u) : h + 1u;
+    L = kind == 0u ? len : 0u;
+    M = kind == 0u ? 0u : len;
+    off = kind == 1u ? ((x >> 5) & 7u) << 8 | ((x >> 8) & 255u) : (x >> 8) & 0xffffu;
   }
-  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return tok_size(b0) == kTokStop; }
+  __device__ static __forceinline__ bool is_stop(uint32_t b0) {
+    const uint32_t kind = b0 & 3u, h = b0 >> 2;
+    return kind == 3u || (kind == 0u && h >= 31u) || (kind == 2u && h >= 32u);
+  }
 };
 
 // ---------------------------------------------------------------------------
 // Block path.  One call parses up to kBlkBytes of compressed input and executes its tokens.
 //
-//   1. stage   lane l loads its 32-byte segment of the block (16-byte aligned base) and stores it to
-//              shared memory; kBlkPad more bytes cover tokens that start in the last segment.
-//   2. chain   every lane computes, right to left over its own 32 bytes (held in registers, fully
+//   1. stage   lane l loads its 32-byte segment of the block (16-byte aligned base), stores it to
+//              shared memory together with the token size every byte would have as a tag (sizes4);
+//              kBlkPad more bytes cover tokens that start in the last segment.
+//   2. chain   every lane computes, right to left over its own 32 size bytes (in registers, fully
 //              unrolled), where a token chain entering its segment at byte p leaves it: a 32-entry
-//              exit table per lane.  The true entry of every segment then follows by walking the 32
-//              tables from the known entry of segment 0.  No speculation, no retries.
-//   3. walk    each lane walks the tokens of its segment twice: count them / sum their output
-//              lengths, and after one warp scan write one record per token (block position | output
-//              position) in stream order.
-//   4. execute 32 consecutive tokens per step, one per lane: literals, then matches in dependency
-//              rounds: a match runs as soon as the tokens of this step that produce its source bytes
-//              have run (sources below the step are final).
+//              exit table per lane.  The true entry of every segment is the fixpoint of
+//              entry[l] = exit[l-1][entry[l-1]] with entry[0] known: one shuffle + one table lookup
+//              per round, as many rounds as mis-guessed entries survive (streams re-synchronise
+//              within a few tokens), at most 32.
+//   3. walk    each lane walks the tokens of its segment (size bytes only): count, warp scan, then
+//              the positions of all tokens of the block are listed in stream order.
+//   4. execute 32 consecutive tokens per step, one per lane: a warp scan of the output lengths
+//              places them, literals come from the staged block, matches run in dependency rounds:
+//              a match runs as soon as the tokens of this step that produce its source bytes have
+//              run (sources below the step are final).
 // ---------------------------------------------------------------------------
 constexpr uint32_t kSegBytes = 32;
 constexpr uint32_t kBlkBytes = 32 * kSegBytes;
 constexpr uint32_t kBlkPad = 32;
 constexpr uint32_t kBlkStage = kBlkBytes + kBlkPad;
-constexpr uint32_t kMaxStepOut = 1024;              // output bytes one step may append (ring reach depends on it)
+constexpr uint32_t kMaxStepOut = 32 * kMaxTokOut;   // output bytes one step may append (the ring reach depends on it)
 constexpr uint32_t kSmemIn = kRingBytes;            // staged block
-constexpr uint32_t kSmemRec = kSmemIn + kBlkStage;  // token records (4 B each); the exit tables alias them
-constexpr uint32_t kRecBytes = 4 * (kBlkBytes / 2); // a token is at least 2 bytes
-constexpr uint32_t kLzWarpSmem = kSmemRec + kRecBytes;
+constexpr uint32_t kSmemSz = kSmemIn + kBlkStage;   // token size of every block byte
+constexpr uint32_t kSmemRec = kSmemSz + kBlkBytes;  // exit tables (1 B x 1024), then token positions (2 B x 512)
+constexpr uint32_t kLzWarpSmem = kSmemRec + kBlkBytes;
 static_assert(kRingReach + kMaxStepOut + 16 <= kRingBytes, "ring reach");
-static_assert(kSmemRec % 16 == 0, "record alignment");
+static_assert(kSmemSz % 16 == 0 && kSmemRec % 16 == 0, "alignment");
 
 // Returns the number of tokens retired (0: nothing done, the caller takes the serial path), -1 on a
 // malformed stream.
@@ -178,13 +197,15 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
   uint32_t nl = (avail - kBlkPad) / kSegBytes;                // segments that lie (with the pad) inside the stream
   if (nl > 32u) nl = 32u;
   const uint8_t* const abase = ipp - mis;
-  const uint32_t blk = s.ring + kSmemIn, rec = s.ring + kSmemRec;
+  const uint32_t blk = s.ring + kSmemIn, szs = s.ring + kSmemSz, rec = s.ring + kSmemRec;
 
   // ---- 1. stage ------------------------------------------------------------------------------
   uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
   if (ul < nl) {
     a0 = ld_nc_v4((const uint4*)(abase + kSegBytes * ul));
     a1 = ld_nc_v4((const uint4*)(abase + kSegBytes * ul + 16u));
+  }
+  if (ul < nl) {                                              // (the segment of lane nl is the pad: lanes 0/1 fill it)
     sts_v4(blk + kSegBytes * ul, a0);
     sts_v4(blk + kSegBytes * ul + 16u, a1);
   }
@@ -192,107 +213,148 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
     const uint4 pad = ld_nc_v4((const uint4*)(abase + kSegBytes * nl + 16u * ul));
     sts_v4(blk + kSegBytes * nl + 16u * ul, pad);
   }
-  // ---- 2. chain: exit table of this lane's segment ---------------------------------------------
-  {
-    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const uint32_t ex = rec + kSegBytes * ul;
+  // Per-lane byte arrays (token sizes, exit table) use a lane-private bank layout: byte p of lane l lives in
+  // word (p >> 2) * 32 + l, i.e. every lane stays in its own shared-memory bank whatever p it indexes
+  // (32-byte rows per lane would put eight lanes on one bank).
+  uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const uint32_t my_sz = szs + 4u * ul, my_ex = rec + 4u * ul;
 #pragma unroll
-    for (int p = 31; p >= 0; --p) {
-      const uint32_t b = (w[p >> 2] >> (8 * (p & 3))) & 255u;
-      const uint32_t sz = P::tok_size(b);
-      const uint32_t q = (uint32_t)p + sz;
-      uint32_t code;
-      if (q >= kSegBytes) code = (sz == kTokStop) ? 0xffu : q - kSegBytes;
-      else code = lds_u8(ex + q);
-      sts_u8(ex + (uint32_t)p, code);
-    }
+  for (int i = 0; i < 8; ++i) {
+    w[i] = P::sizes4(w[i]);
+    sts_u32(my_sz + 128u * i, w[i]);
+  }
+  // ---- 2. chain: exit table of this lane's segment (code >= 32: the chain ends in a stop token) ----
+#pragma unroll
+  for (int p = 31; p >= 0; --p) {
+    const uint32_t q = (uint32_t)p + ((w[p >> 2] >> (8 * (p & 3))) & 255u);
+    const uint32_t code = (q >= kSegBytes) ? q - kSegBytes : lds_u8(my_ex + lane_private(q));
+    sts_u8(my_ex + (uint32_t)(128 * (p >> 2) + (p & 3)), code);
   }
   __syncwarp();
-  // entry of every segment: walk the tables from the known entry of segment 0 (warp-uniform)
-  uint32_t e = mis, my_e = 0, stop_lane = 32u;
-  for (uint32_t l = 0; l < nl; ++l) {
-    if (ul == l) my_e = e;
-    const uint32_t x = lds_u8(rec + kSegBytes * l + e);
-    if (x == 0xffu) { stop_lane = l; break; }
-    e = x;
+  // entry of every segment: fixpoint of e[l] = exit[l-1][e[l-1]], e[0] = mis.  A stop exit hands the next
+  // lane entry 0: lanes behind a stop are ignored below, this only keeps the iteration short.
+  uint32_t e = ul == 0u ? mis : 0u;
+  {
+    const uint32_t prev = my_ex - 4u;
+    while (true) {
+      const uint32_t pe = __shfl_up_sync(kFull, e, 1);
+      uint32_t ne = mis;
+      if (ul != 0u) { ne = lds_u8(prev + lane_private(pe)); if (ne >= kSegBytes) ne = 0u; }
+      const bool changed = ne != e;
+      e = ne;
+      if (!__any_sync(kFull, changed)) break;
+    }
   }
-  // ---- 3. walk: token count / output bytes of this lane's segment -------------------------------
+  const uint32_t my_exit = lds_u8(my_ex + lane_private(e));
+  const unsigned stopm = __ballot_sync(kFull, ul < nl && my_exit >= kSegBytes);
+  const uint32_t stop_lane = stopm ? (uint32_t)__ffs((int)stopm) - 1u : 32u;
+  // ---- 3. walk: tokens of this lane's segment ------------------------------------------------------
   const bool active = ul < nl && ul <= stop_lane;
-  uint32_t p = my_e, cnt = 0, osum = 0;
+  uint32_t p = e, cnt = 0;
   if (active) {
     while (p < kSegBytes) {
-      const uint32_t b = lds_u8(blk + kSegBytes * ul + p);
-      const uint32_t sz = P::tok_size(b);
+      const uint32_t sz = lds_u8(my_sz + lane_private(p));
       if (sz == kTokStop) break;
       ++cnt;
-      osum += P::tok_out(b);
       p += sz;
     }
   }
   // block end: the stop token, or where the chain leaves the last segment
-  const uint32_t end_pos = stop_lane < 32u ? __shfl_sync(kFull, kSegBytes * ul + p, (int)stop_lane)
-                                           : kSegBytes * nl + e;
-  uint32_t incl = cnt | (osum << 10);                           // cnt <= 16 per lane, osum <= 16 * 64
+  const uint32_t end_pos = __shfl_sync(kFull, kSegBytes * ul + p, (int)(stop_lane < 32u ? stop_lane : nl - 1u));
+  uint32_t incl = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t o = __shfl_up_sync(kFull, incl, d);
     if (lane >= d) incl += o;
   }
-  const uint32_t tot = __shfl_sync(kFull, incl, 31);
-  const uint32_t N = tot & 1023u, total_out = tot >> 10;
+  const uint32_t N = __shfl_sync(kFull, incl, 31);
   if (N == 0u) return 0;
-  if ((uint64_t)s.op + total_out > s.out_cap) return 0;         // the serial path finds the exact error
-  __syncwarp();                                                 // exit tables are dead: records overwrite them
+  __syncwarp();                                                 // exit tables are dead: positions overwrite them
   {
-    uint32_t t = (incl & 1023u) - cnt, run = (incl >> 10) - osum, q = my_e;
+    uint32_t ra = rec + 2u * (incl - cnt), q = e;
     for (uint32_t j = 0; j < cnt; ++j) {
-      const uint32_t b = lds_u8(blk + kSegBytes * ul + q);
-      sts_u32(rec + 4u * t, (kSegBytes * ul + q) | (run << 10));
-      run += P::tok_out(b);
-      q += P::tok_size(b);
-      ++t;
+      sts_u16(ra, kSegBytes * ul + q);
+      q += lds_u8(my_sz + lane_private(q));
+      ra += 2u;
     }
   }
   __syncwarp();
 
   // ---- 4. execute ------------------------------------------------------------------------------
   // Output positions are kept in "aligned space" (offset + s.align): the ring index is (pos & mask)
-  // and (s.out - s.align)[pos] is the global address.
+  // and (s.out - s.align)[pos] is the global address.  Every lane moves at most 8 literal and 8 match
+  // bytes of its token itself; what a longer token has beyond that is moved by the whole warp, one
+  // token at a time (a long token must not make 31 short ones loop).
   const uint32_t rbase = s.ring;
   const uint8_t* const outa = s.out - s.align;
-  const uint32_t out0 = s.op + s.align;
-  uint32_t t0 = 0;
-  while (t0 < N) {
-    const uint32_t t = t0 + ul;
-    bool valid = t < N;
-    const uint32_t r = lds_u32(rec + 4u * (valid ? t : t0));
-    const uint32_t pos = r & 1023u;
-    const uint32_t dst = out0 + (r >> 10);
+  const uint32_t cap_left0 = (uint32_t)min(s.out_cap - s.op, (uint64_t)0xffffffffu);
+  uint32_t produced = 0;
+  for (uint32_t t0 = 0; t0 < N; t0 += 32u) {
+    const bool valid = ul < N - t0;
+    const uint32_t pos = lds_u16(rec + 2u * (t0 + (valid ? ul : 0u)));
     uint32_t L, M, off, lit_at;
     P::fields(blk, pos, L, M, off, lit_at);
-    const uint32_t step_lo = __shfl_sync(kFull, dst, 0);
-    // tokens of this step: the leading run that ends within kMaxStepOut bytes (never empty)
-    const unsigned fitm = __ballot_sync(kFull, valid && dst + L + M - step_lo <= kMaxStepOut);
-    const uint32_t n = fitm == kFull ? 32u : (uint32_t)__ffs((int)~fitm) - 1u;
-    valid = ul < n;
     if (!valid) { L = 0; M = 0; }
-    const uint32_t step_hi = __shfl_sync(kFull, dst + L + M, (int)n - 1);
+    const uint32_t len = L + M;
+    uint32_t run = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(kFull, run, d);
+      if (lane >= d) run += o;
+    }
+    const uint32_t step_out = __shfl_sync(kFull, run, 31);
+    if (step_out > cap_left0 - produced) return -1;
+    const uint32_t step_lo = s.op + s.align;
+    const uint32_t dst = step_lo + run - len;
     const uint32_t o_mat = dst + L;
     const bool has = M != 0u;
-    if (__any_sync(kFull, has && (off == 0u || off > o_mat - s.align))) return -1;
-    // literals: straight from the staged block
-    for (uint32_t j = 0; __any_sync(kFull, j < L); ++j)
-      if (j < L) sts_u8(rbase + ((dst + j) & kRingMask), lds_u8(blk + lit_at + j));
+    // off == 0 or beyond the bytes produced so far: malformed (off - 1 wraps to 0xffffffff for off == 0)
+    if (__any_sync(kFull, has && off - 1u >= o_mat - s.align)) return -1;
+    // a token that crosses the end of the ring goes byte-wise with masked indices
+    const uint32_t didx_l = dst & kRingMask;
+    const bool wrap = didx_l + len > kRingBytes;
+    // ---- literals
+    const unsigned litm = __ballot_sync(kFull, L != 0u);
+    if (litm) {
+      const uint32_t la = blk + lit_at, ld = rbase + didx_l;
+      if (L != 0u && !wrap) {
+        const uint32_t x0 = lds_u8<0>(la), x1 = lds_u8<1>(la), x2 = lds_u8<2>(la), x3 = lds_u8<3>(la);
+        sts_u8<0>(ld, x0);
+        if (L > 1u) sts_u8<1>(ld, x1);
+        if (L > 2u) sts_u8<2>(ld, x2);
+        if (L > 3u) sts_u8<3>(ld, x3);
+      }
+      unsigned longl = __ballot_sync(kFull, L > 4u || (L != 0u && wrap));
+      if (longl) {
+        if (L > 4u && !wrap) {
+          const uint32_t x0 = lds_u8<4>(la), x1 = lds_u8<5>(la), x2 = lds_u8<6>(la), x3 = lds_u8<7>(la);
+          sts_u8<4>(ld, x0);
+          if (L > 5u) sts_u8<5>(ld, x1);
+          if (L > 6u) sts_u8<6>(ld, x2);
+          if (L > 7u) sts_u8<7>(ld, x3);
+        }
+        longl = __ballot_sync(kFull, L > 8u || (L != 0u && wrap));
+        while (longl) {                                        // whole warp: the rest of one long literal per round
+          const int t = __ffs((int)longl) - 1;
+          longl &= longl - 1u;
+          const uint32_t tL = __shfl_sync(kFull, L, t), tla = __shfl_sync(kFull, la, t), td = __shfl_sync(kFull, dst, t);
+          const uint32_t j0 = __shfl_sync(kFull, wrap ? 0u : 8u, t);
+          const uint32_t j = j0 + ul;                          // L <= 31: one round
+          if (j < tL) sts_u8(rbase + ((td + j) & kRingMask), lds_u8(tla + j));
+        }
+      }
+    }
     __syncwarp();
-    // matches
+    // ---- matches
     const unsigned hasm = __ballot_sync(kFull, has);
     if (hasm) {
-      const uint32_t cur_op = step_lo - s.align;
+      const uint32_t cur_op = s.op;
       const uint32_t ring_from = max(s.ring_lo, cur_op > kRingReach ? cur_op - kRingReach : 0u) + s.align;
       const uint32_t src = o_mat - off;
       const uint32_t src_end = src + min(M, off);              // exclusive end of the bytes this match reads
       // which tokens of this step produce my source bytes?  Token ranges are consecutive, so the
-      // producers are the lanes from the one holding byte max(src, step_lo) to the one holding src_end-1.
+      // producers are the lanes from the one holding byte max(src, step_lo) to the one holding src_end-1
+      // (own literals precede the own match in program order: the self bit is dropped).
       unsigned dep = 0;
       const bool inwin = has && src_end > step_lo;
       if (__any_sync(kFull, inwin)) {
@@ -306,60 +368,66 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
           if (va <= qa) ja += st;
           if (vb <= qb) jb += st;
         }
-        // own literals precede the own match in program order: drop the self bit
         if (inwin) dep = ((2u << jb) - 1u) & ~((1u << ja) - 1u) & ~(1u << ul);
       }
-      const uint32_t didx = o_mat & kRingMask, sidx = src & kRingMask;
-      const bool in_ring = src >= ring_from && sidx + M + 4u <= kRingBytes;
+      const uint32_t sidx = src & kRingMask;
+      const bool in_ring = src >= ring_from && sidx + M + 8u <= kRingBytes;
       const bool far = src + M <= ring_from;                   // flushed long ago: read from global memory
-      // groups of four bytes are loaded, then stored: needs off >= 4 (a shorter period takes the byte loop)
-      const bool simple = has && off >= 4u && didx + M <= kRingBytes && (in_ring || far);
-      const uint32_t dp = rbase + didx, sp = rbase + sidx;
-      const uint8_t* const gp = outa + src;
-      unsigned done = ~hasm;
-      bool pend = has;
-      while (true) {
-        const bool ready = pend && (dep & ~done) == 0u;
-        const unsigned rm = __ballot_sync(kFull, ready);
-        const bool fr = ready && simple && !far, fg = ready && simple && far, gen = ready && !simple;
-        if (fr) {
-          const uint32_t x0 = lds_u8<0>(sp), x1 = lds_u8<1>(sp), x2 = lds_u8<2>(sp), x3 = lds_u8<3>(sp);
-          sts_u8<0>(dp, x0);
-          if (M > 1u) sts_u8<1>(dp, x1);
-          if (M > 2u) sts_u8<2>(dp, x2);
-          if (M > 3u) sts_u8<3>(dp, x3);
-        }
-        for (uint32_t g = 4; __any_sync(kFull, fr && M > g); g += 4) {
-          if (fr && M > g) {
-            const uint32_t s4 = sp + g, d4 = dp + g;
-            const uint32_t x0 = lds_u8<0>(s4), x1 = lds_u8<1>(s4), x2 = lds_u8<2>(s4), x3 = lds_u8<3>(s4);
+      // groups of four bytes are loaded, then stored: needs off >= 4 and M >= 4 (shorter periods / copies
+      // and anything that crosses the end of the ring take the byte loop)
+      const bool simple = !wrap && off >= 4u && M >= 4u && (in_ring || far);
+      const bool c_r = has && simple && !far, c_g = has && simple && far, c_b = has && !simple;
+      const uint32_t dp = rbase + (o_mat & kRingMask);
+      // sources flushed long ago are final: those matches run first, outside the rounds
+      if (__any_sync(kFull, c_g)) {
+        if (c_g) {
+          const uint8_t* const gp = outa + src;
+          for (uint32_t g = 0; g < M; g += 4u) {
+            const uint8_t* const g4 = gp + g;
+            const uint32_t d4 = dp + g;
+            uint32_t x1 = 0, x2 = 0, x3 = 0;
+            const uint32_t x0 = ldg_u8<0>(g4);
+            if (M > g + 1u) x1 = ldg_u8<1>(g4);
+            if (M > g + 2u) x2 = ldg_u8<2>(g4);
+            if (M > g + 3u) x3 = ldg_u8<3>(g4);
             sts_u8<0>(d4, x0);
             if (M > g + 1u) sts_u8<1>(d4, x1);
             if (M > g + 2u) sts_u8<2>(d4, x2);
             if (M > g + 3u) sts_u8<3>(d4, x3);
           }
         }
-        if (__any_sync(kFull, fg)) {
-          for (uint32_t g = 0; __any_sync(kFull, fg && M > g); g += 4) {
-            if (fg && M > g) {
-              const uint8_t* const g4 = gp + g;
-              const uint32_t d4 = dp + g;
-              uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-              x0 = ldg_u8<0>(g4);
-              if (M > g + 1u) x1 = ldg_u8<1>(g4);
-              if (M > g + 2u) x2 = ldg_u8<2>(g4);
-              if (M > g + 3u) x3 = ldg_u8<3>(g4);
-              sts_u8<0>(d4, x0);
-              if (M > g + 1u) sts_u8<1>(d4, x1);
-              if (M > g + 2u) sts_u8<2>(d4, x2);
-              if (M > g + 3u) sts_u8<3>(d4, x3);
-            }
+        __syncwarp();                                           // their bytes may feed round 1
+      }
+      const unsigned m_b = __ballot_sync(kFull, c_b);
+      const unsigned m_4 = __ballot_sync(kFull, c_r && M > 4u);
+      const unsigned m_8 = __ballot_sync(kFull, c_r && M > 8u);
+      unsigned done = ~__ballot_sync(kFull, c_r || c_b);
+      bool pend = c_r || c_b;
+      const uint32_t sa = rbase + (sidx & ~3u), sh = (sidx & 3u) * 8u;   // aligned words around the source
+      while (done != kFull) {
+        const bool ready = pend && (dep & ~done) == 0u;
+        const unsigned rm = __ballot_sync(kFull, ready);
+        const bool go = ready && c_r;
+        if (go) {
+          const uint32_t x = __funnelshift_r(lds_u32(sa), lds_u32(sa + 4u), sh);
+          sts_u8<0>(dp, x);
+          sts_u8<1>(dp, x >> 8);
+          sts_u8<2>(dp, x >> 16);
+          sts_u8<3>(dp, x >> 24);
+        }
+        if (rm & m_4) {
+          if (go && M > 4u) {                                  // (reloaded: with off < 8 these are bytes stored just above)
+            const uint32_t x = __funnelshift_r(lds_u32(sa + 4u), lds_u32(sa + 8u), sh);
+            sts_u8<4>(dp, x);
+            if (M > 5u) sts_u8<5>(dp, x >> 8);
+            if (M > 6u) sts_u8<6>(dp, x >> 16);
+            if (M > 7u) sts_u8<7>(dp, x >> 24);
           }
         }
-        if (__any_sync(kFull, gen)) {
-          // short periods, ring wrap-around, sources straddling the flushed boundary: byte by byte,
+        if (rm & m_b) {
+          // short periods / copies, ring wrap-around, sources straddling the flushed boundary: byte by byte,
           // in order (a byte may read what this loop wrote off bytes earlier)
-          if (gen) {
+          if (ready && c_b) {
             for (uint32_t j = 0; j < M; ++j) {
               const uint32_t q = src + j;
               const uint32_t b = (q >= ring_from) ? lds_u8(rbase + (q & kRingMask)) : (uint32_t)outa[q];
@@ -368,13 +436,26 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
           }
         }
         __syncwarp();
+        unsigned longm = rm & m_8;
+        if (longm) {
+          // bytes 8.. of the long matches that just ran: whole warp, one match per round (M <= 32).  Byte j of an
+          // overlapping match (off < M) repeats byte j mod off.
+          do {
+            const int t = __ffs((int)longm) - 1;
+            longm &= longm - 1u;
+            const uint32_t tM = __shfl_sync(kFull, M, t), toff = __shfl_sync(kFull, off, t);
+            const uint32_t tsp = __shfl_sync(kFull, sidx, t), tdp = __shfl_sync(kFull, dp, t);
+            const uint32_t j = 8u + ul;
+            if (j < tM) sts_u8(tdp + j, lds_u8(rbase + tsp + (toff < tM ? j % toff : j)));
+          } while (longm);
+          __syncwarp();
+        }
         done |= rm;
         pend = pend && !ready;
-        if (done == kFull) break;
       }
     }
-    s.op += step_hi - step_lo;
-    t0 += n;
+    s.op += step_out;
+    produced += step_out;
     lz_flush_blocks(s, lane);
   }
   s.ip += end_pos - mis;

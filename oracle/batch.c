@@ -4,8 +4,23 @@
  */
 #define _GNU_SOURCE
 #include "oracle.h"
+#include <dlfcn.h>
 #include <pthread.h>
 #include <time.h>
+
+/* ORACLE_LIBLZ4: the CPU decoder the reference itself links for its LZ4 known-answer tests
+ * (reference examples/lz4_cpu_decompression.cu:143-147: LZ4_decompress_safe), taken from the box's own
+ * liblz4.so.1 at run time.  Timed next to the port so the LZ4 baseline is the real library. */
+typedef int (*lz4_safe_fn)(const char*, char*, int, int);
+static lz4_safe_fn g_lz4_safe;
+int oracle_have_liblz4(void)
+{
+  if (!g_lz4_safe) {
+    void* h = dlopen("liblz4.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) g_lz4_safe = (lz4_safe_fn)dlsym(h, "LZ4_decompress_safe");
+  }
+  return g_lz4_safe != 0;
+}
 
 long oracle_cascaded_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) __attribute__((weak));
 long oracle_bitcomp_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) __attribute__((weak));
@@ -41,6 +56,7 @@ static void* worker(void* p)
     case ORACLE_CASCADED: if (oracle_cascaded_decompress) r = oracle_cascaded_decompress(s, j->len[i], d, j->stride); break;
     case ORACLE_BITCOMP: if (oracle_bitcomp_decompress) r = oracle_bitcomp_decompress(s, j->len[i], d, j->stride); break;
     case ORACLE_ANS: if (oracle_ans_decompress) r = oracle_ans_decompress(s, j->len[i], d, j->stride); break;
+    case ORACLE_LIBLZ4: if (g_lz4_safe) r = g_lz4_safe((const char*)s, (char*)d, (int)j->len[i], (int)j->stride); break;
     default: break;
     }
     if (r < 0) { j->failed = 1; r = 0; }
@@ -56,6 +72,7 @@ double oracle_batch_decompress(int codec, const uint8_t* comp, const size_t* com
 {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
+  if (codec == ORACLE_LIBLZ4 && !oracle_have_liblz4()) return -1.0;
   pthread_t th[256];
   job_t jobs[256];
   struct timespec t0, t1;

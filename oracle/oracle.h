@@ -43,7 +43,9 @@ long oracle_snappy_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t c
 size_t oracle_snappy_bound(size_t n);
 
 /* codec ids for the threaded batch runner */
-enum { ORACLE_LZ4 = 0, ORACLE_SNAPPY = 1, ORACLE_CASCADED = 2, ORACLE_BITCOMP = 3, ORACLE_ANS = 4 };
+enum { ORACLE_LZ4 = 0, ORACLE_SNAPPY = 1, ORACLE_CASCADED = 2, ORACLE_BITCOMP = 3, ORACLE_ANS = 4,
+       ORACLE_LIBLZ4 = 5 /* liblz4.so.1's LZ4_decompress_safe (dlopen), not the port */ };
+int oracle_have_liblz4(void);
 
 /* Decompress `count` chunks with `nthreads` pthreads (contiguous chunk range per
  * thread, SURVEY.md 8d "CPU baseline").  comp = base pointer of a slab,

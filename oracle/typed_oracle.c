@@ -137,14 +137,20 @@ long oracle_cascaded_decompress(const uint8_t* src, size_t n, uint8_t* dst, size
   unsigned type = cfg & 0xff; int R = (cfg >> 8) & 0xff, D = (cfg >> 16) & 0xff;
   unsigned ts = type_size(type);
   uint32_t ulen = rd32(src + 8), P = rd32(src + 12), np = rd32(src + 16);
-  if (!ts || R > 7 || D > 7 || P == 0 || P > 16384 || (P % ts) || (ulen % ts)) return -1;
-  if ((uint64_t)np * P < ulen || (np && (uint64_t)(np - 1) * P >= ulen)) return -1;
+  if (!ts || R > 7 || D > 7 || P < 512 || P > 16384 || (P % 8)) return -1;
+  uint32_t tail = ulen % ts, whole = ulen - tail;   /* partitions cover the whole elements */
+  if ((uint64_t)np * P < whole || (np && (uint64_t)(np - 1) * P >= whole)) return -1;
   if (20 + 4 * ((size_t)np + 1) > n || ulen > cap) return -1;
   for (uint32_t p = 0; p < np; ++p) {
     uint32_t o0 = rd32(src + 20 + 4 * p), o1 = rd32(src + 20 + 4 * (p + 1));
     if ((o0 & 7) || o0 > o1 || o1 > n) return -1;
-    uint32_t begin = p * P, nb = ulen - begin < P ? ulen - begin : P;
+    uint32_t begin = p * P, nb = whole - begin < P ? whole - begin : P;
     if (casc_decode_part(src + o0, o1 - o0, dst + begin, nb / ts, ts, R, D, P / ts) < 0) return -1;
+  }
+  if (tail) {   /* trailing bytes: one verbatim word after the last partition */
+    uint32_t to = rd32(src + 20 + 4 * np);
+    if ((uint64_t)to + 8 > n) return -1;
+    memcpy(dst + whole, src + to, tail);
   }
   return (long)ulen;
 }
@@ -192,8 +198,9 @@ long oracle_cascaded_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t
                               int R, int D, int use_bp)
 {
   unsigned ts = type_size(type);
-  if (!ts || (n % ts) || P == 0 || (P % ts)) return -1;
-  size_t np = (n + P - 1) / P;
+  if (!ts || P < 512 || P > 16384 || (P % 8)) return -1;
+  size_t tail = n % ts, whole = n - tail;
+  size_t np = (whole + P - 1) / P;
   size_t off = (20 + 4 * (np + 1) + 7) & ~(size_t)7;
   if (cap < off) return -1;
   wr32(dst, CSC_MAGIC);
@@ -205,7 +212,7 @@ long oracle_cascaded_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t
   uint64_t* rl = (uint64_t*)malloc(8 * (cap_e + 1));
   for (size_t p = 0; p < np; ++p) {
     wr32(dst + 20 + 4 * p, (uint32_t)off);
-    size_t begin = p * P, nb = n - begin < P ? n - begin : P;
+    size_t begin = p * P, nb = whole - begin < P ? whole - begin : P;
     size_t count = nb / ts;
     for (size_t k = 0; k < count; ++k) cur[k] = load_ts(src + begin + k * ts, ts);
     uint8_t* q = dst + off;
@@ -243,6 +250,12 @@ long oracle_cascaded_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t
   }
   wr32(dst + 20 + 4 * np, (uint32_t)off);
   free(cur); free(nxt); free(rl);
+  if (tail) {
+    if (cap < off + 8) return -1;
+    memset(dst + off, 0, 8);
+    memcpy(dst + off, src + whole, tail);
+    off += 8;
+  }
   return (long)off;
 }
 
@@ -262,7 +275,7 @@ long oracle_bitcomp_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_
   unsigned algo = rd32(src + 4) & 0xff, type = (rd32(src + 4) >> 8) & 0xff;
   unsigned ts = type_size(type);
   uint32_t ulen = rd32(src + 8), nblocks = rd32(src + 12);
-  if (!ts || algo > 1 || (ulen % ts) || ulen > cap) return -1;
+  if (!ts || algo > 1 || ulen > cap) return -1;
   size_t ne = ulen / ts;
   if (nblocks != (ne + 127) / 128 || 16 + 2 * (size_t)nblocks > n) return -1;
   size_t off = (16 + 2 * (size_t)nblocks + 7) & ~(size_t)7;
@@ -287,6 +300,7 @@ long oracle_bitcomp_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_
       size_t bytes = 16 + 8 * (((size_t)nz * bits + 63) / 64);
       if (off + bytes > n) return -1;
       uint64_t mlo = rd64(src + off), mhi = rd64(src + off + 8);
+      if ((unsigned)(__builtin_popcountll(mlo) + __builtin_popcountll(mhi)) != nz) return -1;
       unsigned rank = 0;
       for (size_t k = 0; k < nv; ++k) {
         int set = (int)(((k < 64 ? mlo >> k : mhi >> (k - 64))) & 1);
@@ -297,6 +311,12 @@ long oracle_bitcomp_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_
       off += bytes;
     }
     if (err) return -1;
+  }
+  /* trailing bytes of a chunk whose length is not a multiple of the element size: one verbatim word */
+  size_t tail = ulen - ne * ts;
+  if (tail) {
+    if (off + 8 > n) return -1;
+    memcpy(dst + ne * ts, src + off, tail);
   }
   return (long)ulen;
 }
@@ -313,8 +333,8 @@ long oracle_bitcomp_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t 
   if (!ts || algo > 1) return -1;
   size_t ne = n / ts, nblocks = (ne + 127) / 128;
   size_t off = (16 + 2 * nblocks + 7) & ~(size_t)7;
-  if (cap < off + nblocks * (16 + 128 * (size_t)ts)) return -1;
-  wr32(dst, BTC_MAGIC); wr32(dst + 4, algo | (type << 8)); wr32(dst + 8, (uint32_t)(ne * ts));
+  if (cap < off + nblocks * (16 + 128 * (size_t)ts) + 8) return -1;
+  wr32(dst, BTC_MAGIC); wr32(dst + 4, algo | (type << 8)); wr32(dst + 8, (uint32_t)n);
   wr32(dst + 12, (uint32_t)nblocks);
   memset(dst + 16, 0, off - 16);
   for (size_t b = 0; b < nblocks; ++b) {
@@ -355,6 +375,11 @@ long oracle_bitcomp_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t 
     }
     dst[16 + 2 * b] = (uint8_t)(desc & 255); dst[17 + 2 * b] = (uint8_t)(desc >> 8);
   }
+  if (n - ne * ts) {
+    memset(dst + off, 0, 8);
+    memcpy(dst + off, src + ne * ts, n - ne * ts);
+    off += 8;
+  }
   return (long)off;
 }
 
@@ -384,7 +409,7 @@ long oracle_ans_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t ca
   }
   for (uint32_t sg = 0; sg < nseg; ++sg) {
     uint32_t o0 = rd32(src + 528 + 4 * sg), o1 = rd32(src + 528 + 4 * (sg + 1));
-    if ((o0 & 3) || o0 + 128 > o1 || o1 > n) return -1;
+    if ((o0 & 3) || o0 > o1 || o1 > n || o1 - o0 < 128) return -1;
     uint32_t x[32];
     for (int l = 0; l < 32; ++l) x[l] = rd32(src + o0 + 4 * l);
     const uint8_t* words = src + o0 + 128;

@@ -57,6 +57,15 @@ static void roundtrip(nvcompManagerBase& mgr, const std::vector<uint8_t>& host, 
   CK(cudaFree(d_in)); CK(cudaFree(d_comp)); CK(cudaFree(d_out));
 }
 
+static uint32_t host_crc32(const uint8_t* p, size_t n) {     // zlib / IEEE 802.3
+  uint32_t c = 0xffffffffu;
+  for (size_t i = 0; i < n; ++i) {
+    c ^= p[i];
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xedb88320u : c >> 1;
+  }
+  return c ^ 0xffffffffu;
+}
+
 int main() {
   cudaStream_t stream; CK(cudaStreamCreate(&stream));
   const size_t sizes[] = {0, 1, 65535, 65536, 65537, 1000000, 5 * 65536};
@@ -69,8 +78,9 @@ int main() {
         const ChecksumPolicy pol = (kind & 1) ? ComputeAndVerify : NoComputeNoVerify;
         if (fmt == 0) m = std::make_shared<LZ4Manager>(1 << 16, nvcompBatchedLZ4Opts_t{NVCOMP_TYPE_CHAR}, stream, 0, pol);
         if (fmt == 1) m = std::make_shared<SnappyManager>(1 << 16, nvcompBatchedSnappyOpts_t{}, stream, 0, pol);
-        if (fmt == 2) { nn = n / 8 * 8; m = std::make_shared<CascadedManager>(1 << 16, nvcompBatchedCascadedOpts_t{4096, NVCOMP_TYPE_LONGLONG, 1, 1, 1}, stream, 0, pol); }
-        if (fmt == 3) { nn = n / 4 * 4; m = std::make_shared<BitcompManager>(1 << 16, nvcompBatchedBitcompFormatOpts{0, NVCOMP_TYPE_UINT}, stream, 0, pol); }
+        // (typed formats take any length: trailing bytes that do not fill an element travel verbatim)
+        if (fmt == 2) { m = std::make_shared<CascadedManager>(1 << 16, nvcompBatchedCascadedOpts_t{4096, NVCOMP_TYPE_LONGLONG, 1, 1, 1}, stream, 0, pol); }
+        if (fmt == 3) { m = std::make_shared<BitcompManager>(1 << 16, nvcompBatchedBitcompFormatOpts{0, NVCOMP_TYPE_UINT}, stream, 0, pol); }
         if (fmt == 4) m = std::make_shared<ANSManager>(1 << 16, nvcompBatchedANSOpts_t{}, stream, 0, pol);
         auto host = make_data(nn, kind, 17 * fmt + kind);
         roundtrip(*m, host, stream, /*via_factory=*/(kind & 2) != 0, (kind & 1) ? NoComputeAndVerifyIfPresent : NoComputeNoVerify,
@@ -93,17 +103,42 @@ int main() {
     std::vector<uint8_t> comp(csize); CK(cudaMemcpy(comp.data(), d_comp, csize, cudaMemcpyDeviceToHost));
     auto dc = mgr.configure_decompression(d_comp);
     uint8_t* d_out; CK(cudaMalloc(&d_out, host.size()));
+    // the stored checksums are the standard CRC-32 of the uncompressed buffer and of everything after the header
+    {
+      uint32_t stored[2];
+      memcpy(stored, comp.data() + 64, 8);
+      REQUIRE(stored[0] == host_crc32(host.data(), host.size()));
+      REQUIRE(stored[1] == host_crc32(comp.data() + 72, csize - 72));
+    }
+    // the compressed checksum covers the size table and every chunk: no flipped bit anywhere in the payload
+    // may come back as success
     bool caught = false;
-    for (size_t pos = csize - 40; pos > csize - 2000 && !caught; pos -= 7) {
+    for (long pos = (long)csize - 40; pos > 80; pos -= (pos > (long)csize - 3000 ? 7 : 9973)) {
       std::vector<uint8_t> bad = comp; bad[pos] ^= 0x01;
       CK(cudaMemcpy(d_comp, bad.data(), csize, cudaMemcpyHostToDevice));
       mgr.decompress(d_out, d_comp, dc);
       CK(cudaStreamSynchronize(stream));
       const nvcompStatus_t st = *dc.get_status();
-      REQUIRE(st == nvcompSuccess || st == nvcompErrorBadChecksum || st == nvcompErrorCannotDecompress);
+      REQUIRE(st == nvcompErrorBadChecksum || st == nvcompErrorCannotDecompress);
       if (st == nvcompErrorBadChecksum) caught = true;
     }
     REQUIRE(caught);
+    // a corrupt header is rejected at configure time, before any pointer is derived from it
+    {
+      auto try_header = [&](size_t off, uint64_t value, size_t bytes) {
+        std::vector<uint8_t> bad = comp;
+        memcpy(bad.data() + off, &value, bytes);
+        CK(cudaMemcpy(d_comp, bad.data(), csize, cudaMemcpyHostToDevice));
+        bool threw_invalid = false;
+        try { mgr.configure_decompression(d_comp); } catch (const NVCompException& e) { threw_invalid = e.get_error() == nvcompErrorInvalidValue; }
+        REQUIRE(threw_invalid);
+      };
+      try_header(48, 1000000u, 4);     // num_chunks far beyond the data
+      try_header(40, 0u, 8);           // chunk_bytes 0
+      try_header(40, 4096u, 8);        // chunk_bytes inconsistent with num_chunks
+      try_header(32, 1ull << 40, 8);   // uncompressed_bytes inconsistent with num_chunks
+      CK(cudaMemcpy(d_comp, comp.data(), csize, cudaMemcpyHostToDevice));
+    }
     // ComputeAndVerify on a buffer without checksums must throw at configure time
     LZ4Manager plain{1 << 16, nvcompBatchedLZ4Opts_t{NVCOMP_TYPE_CHAR}, stream, 0, NoComputeNoVerify};
     plain.compress(d_in, d_comp, cc);

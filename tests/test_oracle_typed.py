@@ -51,3 +51,15 @@ def test_typed_oracle_rejects_garbage(oracle):
     comp = oracle.compress_typed("cascaded", INPUTS["sorted_i64"], type=6, num_RLEs=1, num_deltas=1, use_bp=1)
     assert oracle.decompress("cascaded", comp[: len(comp) // 2], 65536) is None
     assert oracle.decompress("cascaded", comp, 1000) is None
+
+
+@pytest.mark.parametrize("kind", ["cascaded", "bitcomp"])
+def test_oracle_ragged_lengths(oracle, kind):
+    """Chunk lengths that are not a multiple of the element size keep their trailing bytes."""
+    base = INPUTS["sorted_i64"]
+    for type_id in (2, 4, 6):
+        kw = dict(type=type_id, num_RLEs=1, num_deltas=1, use_bp=1) if kind == "cascaded" else dict(algo=1, type=type_id)
+        for n in (0, 1, 3, 7, 9, 1001, 4099, 65533):
+            comp = oracle.compress_typed(kind, base[:n], **kw)
+            assert oracle.size(kind, comp) == n
+            assert oracle.decompress(kind, comp, n) == base[:n], (kind, type_id, n)

@@ -62,6 +62,17 @@ def test_lz4_synth_hlif():
     assert out.count("decompression throughput (GB/s)") == 28
 
 
+@pytest.mark.parametrize("key", ["f32", "i32", "bytes"])
+def test_lz4_cpu_interop_examples(key, data_files):
+    """The reference's known-answer tests of the LZ4 wire format, compiled unchanged (tests/shim/lz4.h only declares
+    liblz4's prototypes): liblz4-HC(12) streams decode on the GPU (examples/lz4_cpu_compression.cu:61-66,121-140) and
+    GPU streams decode with LZ4_decompress_safe (examples/lz4_cpu_decompression.cu:143-157)."""
+    out = _run("lz4_cpu_compression", "-f", data_files[key])
+    assert "decompression validated :)" in out
+    out = _run("lz4_cpu_decompression", "-f", data_files[key])
+    assert "CPU decompression validated :)" in out
+
+
 def test_quickstarts():
     _run("low_level_quickstart_example")
     _run("high_level_quickstart_example")

@@ -84,6 +84,30 @@ def test_bitcomp(oracle, type_id, algo):
     _roundtrip(codec, "bitcomp", _raws(8), oracle, dict(algo=algo, type=type_id))
 
 
+@pytest.mark.parametrize("kind", ["cascaded", "bitcomp"])
+def test_chunk_length_not_a_multiple_of_the_element_size(oracle, kind):
+    """Trailing bytes (length % sizeof(type)) are carried verbatim: every length round-trips, through the LLIF and
+    against the oracle in both directions (they used to be dropped silently)."""
+    from gpu_util import gpu_compress, gpu_decompress
+    from nvcomp_b200._lib import BitcompOpts, CascadedOpts
+    from nvcomp_b200.batched import Codec
+    base = INPUTS["sorted_i64"]
+    raws = [base[:n] for n in (1, 3, 7, 9, 1001, 4099, 40001, 65535, 65533)] + [b""]
+    for type_id in (2, 4, 6):
+        if kind == "cascaded":
+            codec, okw = Codec("Cascaded", opts=CascadedOpts(4096, type_id, 1, 1, 1)), dict(type=type_id, num_RLEs=1, num_deltas=1, use_bp=1)
+        else:
+            codec, okw = Codec("Bitcomp", opts=BitcompOpts(0, type_id)), dict(algo=0, type=type_id)
+        comps, _ = gpu_compress(codec, raws)
+        for c, r in zip(comps, raws):
+            assert oracle.decompress(kind, c, len(r)) == r, (kind, type_id, len(r))
+        outs, actual, status, _ = gpu_decompress(codec, comps, [len(r) for r in raws])
+        assert (status == 0).all() and actual.tolist() == [len(r) for r in raws] and outs == raws, (kind, type_id)
+        ocomps = [oracle.compress_typed(kind, r, **okw) for r in raws]
+        outs, actual, status, _ = gpu_decompress(codec, ocomps, [len(r) for r in raws])
+        assert (status == 0).all() and outs == raws, (kind, type_id)
+
+
 def test_ans(oracle):
     from nvcomp_b200.batched import Codec
     codec = Codec("ANS")

@@ -19,5 +19,11 @@ build() { # name source [extra]
 for f in lz4 snappy cascaded bitcomp ans gdeflate deflate zstd; do build benchmark_${f}_chunked $R/benchmarks/benchmark_${f}_chunked.cu & done
 for f in benchmark_snappy_synth benchmark_lz4_synth benchmark_hlif; do build $f $R/benchmarks/$f.cpp & done
 for f in low_level_quickstart_example high_level_quickstart_example; do build $f $R/examples/$f.cpp & done
+# the LZ4 CPU-interop examples (known-answer tests of the wire format): liblz4.so.1 is on the image, its header is
+# not -> prototype-only shim in tests/shim/
+NV_SAVE="$NV"; NV="$NV -I$ROOT/tests/shim -I$R/examples -l:liblz4.so.1"
+for f in lz4_cpu_compression lz4_cpu_decompression; do build $f $R/examples/$f.cu & done
+wait
+NV="$NV_SAVE"
 wait
 ls -1 | grep -v '\.log$' | wc -l
