@@ -3,16 +3,23 @@
 
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--codec snappy|lz4|cascaded|bitcomp|ans]
 
-One "step" = one nvcompBatched<Fmt>DecompressAsync pass (through the C ABI of libnvcomp.so)
-over one batch of 10,000 x 64 KB synthetic chunks per GPU.  Default workload = BASELINE.json
-configs[1]: Snappy batched decompress, 10,000 x 64 KB synthetic tabular float32 chunks, 1 GPU.
-The metric is the reference's: total uncompressed bytes / (1e9 * seconds), CUDA-event timed around the
-async call (reference benchmarks/benchmark_template_chunked.cuh:519-539,604-607).
+One "step" = one pass of the hot path over one batch of 10,000 x 64 KB synthetic chunks per GPU through the C ABI
+of libnvcomp.so (nvcompBatched<Fmt>DecompressAsync).  Default workload = BASELINE.json configs[1]: Snappy batched
+decompress, 10,000 x 64 KB synthetic tabular float32 chunks, 1 GPU.  The metric is the reference's: total
+uncompressed bytes / (1e9 * seconds), CUDA-event timed around the asynchronous call (reference
+benchmarks/benchmark_template_chunked.cuh:519-539,604-607).
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same work with
-HOST buffers (pinned): H2D of the compressed chunks + decompress + D2H of the decompressed chunks,
-all inside the timed region; `roofline` = algorithmic bytes / event-timed launch duration vs the
-measured HBM peak; `cpu_baseline` = the CPU oracle port on this box's host cores (rank 0, N=1).
+Prints ONE JSON line (rank 0):
+  value          N = 1: device-resident decode throughput.  N > 1: the whole job north_star describes -- rank 0 owns the
+                 compressed slab of every rank's chunk range, scatters it over NCCL (NVLink) in slices on a side stream
+                 while the slices already received are decoded; `decode_only` stands beside it
+  e2e            the same decode with HOST buffers (pinned): H2D + decode + D2H inside the timed region
+  roofline       algorithmic bytes / event-timed launch duration vs the measured HBM peak
+  per_dataset    the survey's own cfg2 definitions: (i) reference gen_data(3), (ii) price-walk float32 column
+  foreign_streams  the same workload compressed on the HOST by an independent codec (pyarrow-snappy / liblz4 default
+                 and HC-12) and decoded on the GPU, parity-gated
+  cpu_baseline   liblz4's LZ4_decompress_safe (LZ4) / the oracle port on this box's host cores, median and best
+  cfg5           (N > 1, or --cfg5) BASELINE configs[4]: LZ4, 80,000 x 64 KB chunks in total, strong scaling
 """
 from __future__ import annotations
 
@@ -32,11 +39,13 @@ sys.path.insert(0, ROOT)
 
 CHUNK = 65536
 CHUNKS_PER_GPU = 10000
+CFG5_TOTAL_CHUNKS = 80000
 FMT = {"lz4": "LZ4", "snappy": "Snappy", "cascaded": "Cascaded", "bitcomp": "Bitcomp", "ans": "ANS"}
-ORACLE_ID = {"lz4": 0, "snappy": 1, "cascaded": 2, "bitcomp": 3, "ans": 4}
+ORACLE_ID = {"lz4": 0, "snappy": 1, "cascaded": 2, "bitcomp": 3, "ans": 4, "liblz4": 5}
 DEFAULT_DATASET = {"lz4": "lz4_mixed", "snappy": "tabular_f32", "cascaded": "sorted_i64",
                    "bitcomp": "sorted_i64", "ans": "lowentropy_bytes"}
-KERNEL_NAME = {"lz4": "lz4_decompress_v2_kernel<10>", "snappy": "snappy_decompress_v2_kernel<10>",
+KERNEL_NAME = {"lz4": "lz4_decompress_v2_kernel (+ lz4_decompress_light_kernel beside it)",
+               "snappy": "snappy_decompress_v2_kernel (+ snappy_decompress_light_kernel beside it)",
                "cascaded": "cascaded_decompress_kernel", "bitcomp": "bitcomp_decompress_kernel",
                "ans": "ans_decompress_kernel"}
 WORKLOAD_NAME = {
@@ -62,6 +71,30 @@ def codec_opts(kind: str, dataset: str):
     if kind == "bitcomp":
         return BitcompOpts(0, Type.ULONGLONG if "i64" in dataset else Type.UINT)
     return None
+
+
+# ----------------------------------------------------------------------------------------------
+# host placement: pin the rank to the NUMA node of its GPU before any pinned allocation
+# ----------------------------------------------------------------------------------------------
+def pin_to_gpu_numa(gpu_index: int) -> dict:
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return {"pinned": False, "why": "no pci bus id"}
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"pinned": False, "why": "numa_node = -1 (single node or not exposed)"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"pinned": True, "numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001 -- placement is best effort, the numbers say whether it mattered
+        return {"pinned": False, "why": f"{type(e).__name__}: {e}"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -117,7 +150,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU oracle (baseline legs only)
+# CPU codecs (baseline legs only): the oracle port and liblz4 through oracle/batch.c's pthread runner
 # ----------------------------------------------------------------------------------------------
 def load_oracle():
     path = os.path.join(ROOT, "oracle", "liboracle.so")
@@ -127,60 +160,79 @@ def load_oracle():
     lib.oracle_batch_decompress.restype = C.c_double
     lib.oracle_batch_decompress.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                             C.c_size_t, C.c_void_p, C.c_int]
+    lib.oracle_have_liblz4.restype = C.c_int
     return lib
 
 
-def cpu_decode_time(lib, kind, comp_host: np.ndarray, offs: np.ndarray, lens: np.ndarray, out_host: np.ndarray,
-                    threads: int) -> float:
+def cpu_decode_time(lib, codec_id, comp_host, offs, lens, out_host, threads) -> float:
     out_len = np.zeros(len(offs), dtype=np.uint64)
-    t = lib.oracle_batch_decompress(ORACLE_ID[kind], comp_host.ctypes.data, offs.ctypes.data, lens.ctypes.data,
+    t = lib.oracle_batch_decompress(codec_id, comp_host.ctypes.data, offs.ctypes.data, lens.ctypes.data,
                                     len(offs), out_host.ctypes.data, CHUNK, out_len.ctypes.data, threads)
     if t < 0 or not (out_len == CHUNK).all():
-        raise RuntimeError("CPU oracle failed to decode the sample")
+        raise RuntimeError("CPU decoder failed on the sample")
     return t
 
 
-def cpu_baseline(kind, comp_host, offs, lens, raw_check: np.ndarray | None, budget_s: float = 4.0):
-    lib = load_oracle()
-    threads = os.cpu_count() or 1
+def cpu_time_stats(lib, codec_id, comp_host, offs, lens, raw_check, threads, steps=None, budget_s=4.0):
+    """The one estimator both the cpu_baseline leg and --impl reference use: wall time of every repetition
+    (oracle/batch.c: last worker finish - first worker start), reported as median and best."""
     n = len(offs)
     out_host = np.empty(n * CHUNK, dtype=np.uint8)
     offs = np.ascontiguousarray(offs, dtype=np.uint64)
     lens = np.ascontiguousarray(lens, dtype=np.uint64)
-    t0 = cpu_decode_time(lib, kind, comp_host, offs, lens, out_host, threads)   # warm-up + correctness
+    cpu_decode_time(lib, codec_id, comp_host, offs, lens, out_host, threads)      # warm-up + correctness
     if raw_check is not None and not np.array_equal(out_host[: raw_check.size], raw_check.reshape(-1)):
-        raise RuntimeError("CPU oracle output differs from the original data")
-    reps, times = 0, []
-    t_start = time.time()
-    while reps < 3 or (time.time() - t_start < budget_s and reps < 200):
-        times.append(cpu_decode_time(lib, kind, comp_host, offs, lens, out_host, threads))
-        reps += 1
-    best = min(times)
-    return {"value": n * CHUNK / best / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-            "sample": f"{n} chunks x 64 KB of this workload, {reps} repetitions, best wall time, "
-                      f"oracle/ C decoder with {threads} pthreads (contiguous chunk range per thread)",
-            "median_GBps": n * CHUNK / float(np.median(times)) / 1e9}
+        raise RuntimeError("CPU decoder output differs from the original data")
+    times, t_start = [], time.time()
+    while (len(times) < steps) if steps else (len(times) < 3 or (time.time() - t_start < budget_s and len(times) < 200)):
+        times.append(cpu_decode_time(lib, codec_id, comp_host, offs, lens, out_host, threads))
+    return {"median_GBps": n * CHUNK / float(np.median(times)) / 1e9, "best_GBps": n * CHUNK / min(times) / 1e9,
+            "reps": len(times), "median_s": float(np.median(times))}
+
+
+def cpu_baseline(kind, comp_host, offs, lens, raw_check):
+    lib = load_oracle()
+    threads = os.cpu_count() or 1
+    n = len(offs)
+    port = cpu_time_stats(lib, ORACLE_ID[kind], comp_host, offs, lens, raw_check, threads)
+    out = {"value": round(port["median_GBps"], 2), "unit": "GB/s", "cores": threads, "kind": "port",
+           "estimator": "median of the repetitions (best beside it); the same estimator as --impl reference",
+           "best_GBps": round(port["best_GBps"], 2),
+           "sample": f"{n} chunks x 64 KB of this workload (the GPU-compressed streams), {port['reps']} repetitions, "
+                     f"oracle/ C decoder, {threads} pthreads (contiguous chunk range per thread)"}
+    if kind == "lz4" and lib.oracle_have_liblz4():
+        ref = cpu_time_stats(lib, ORACLE_ID["liblz4"], comp_host, offs, lens, raw_check, threads)
+        out.update({"value": round(ref["median_GBps"], 2), "best_GBps": round(ref["best_GBps"], 2), "kind": "reference",
+                    "port_median_GBps": round(port["median_GBps"], 2), "port_best_GBps": round(port["best_GBps"], 2),
+                    "sample": f"{n} chunks x 64 KB of this workload, {ref['reps']} repetitions, liblz4.so.1 "
+                              f"LZ4_decompress_safe (the CPU decoder the reference links, examples/lz4_cpu_decompression.cu:"
+                              f"143-147; dlopen), {threads} pthreads; the oracle port is reported beside it"})
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
-def build_workload(kind: str, dataset: str, n_chunks: int, seed_offset: int):
-    """Host data + device batch + compressed batch (compressed on the GPU through the C ABI)."""
-    import torch
+# workload construction
+# ----------------------------------------------------------------------------------------------
+def gen_data(dataset: str, n_chunks: int, seed_offset: int = 0):
     from nvcomp_b200 import datagen
-    from nvcomp_b200.batched import Batch, Codec
+    if ":" in dataset:
+        name, col = dataset.split(":")
+        return datagen.tabular_f32(n_chunks, column=int(col), **({"seed": 1000 * seed_offset + 1} if seed_offset else {}))
     gen = datagen.DATASETS[dataset]
     try:
-        data = gen(n_chunks, seed=1000 * seed_offset + gen.__defaults__[0]) if seed_offset else gen(n_chunks)
+        return gen(n_chunks, seed=1000 * seed_offset + gen.__defaults__[0]) if seed_offset else gen(n_chunks)
     except TypeError:
-        data = gen(n_chunks)
+        return gen(n_chunks)
+
+
+def device_batch(data: np.ndarray):
+    import torch
+    from nvcomp_b200.batched import Batch
+    n = data.shape[0]
     slab = torch.from_numpy(data.reshape(-1)).cuda()
-    offsets = np.arange(n_chunks, dtype=np.int64) * CHUNK
-    inp = Batch(slab, torch.from_numpy(offsets + slab.data_ptr()).cuda(),
-                torch.full((n_chunks,), CHUNK, dtype=torch.int64, device="cuda"), offsets)
-    codec = Codec(FMT[kind], opts=codec_opts(kind, dataset))
-    comp = codec.compress(inp, max_chunk=CHUNK)
-    torch.cuda.synchronize()
-    return data, inp, codec, comp
+    offsets = np.arange(n, dtype=np.int64) * CHUNK
+    return Batch(slab, torch.from_numpy(offsets + slab.data_ptr()).cuda(),
+                 torch.full((n,), CHUNK, dtype=torch.int64, device="cuda"), offsets)
 
 
 def compact(comp, align=16):
@@ -197,113 +249,305 @@ def compact(comp, align=16):
     return dense, offs, sizes
 
 
+def host_slab_to_batch(chunks):
+    """list of bytes -> (dense device slab, offsets, sizes) in the same 16-byte aligned packing as compact()."""
+    import torch
+    sizes = np.array([len(c) for c in chunks], dtype=np.int64)
+    al = (sizes + 15) // 16 * 16
+    offs = np.concatenate([[0], np.cumsum(al)[:-1]]).astype(np.int64)
+    host = np.zeros(int(al.sum()) + 64, dtype=np.uint8)
+    for c, o in zip(chunks, offs):
+        host[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+    return torch.from_numpy(host).cuda(), offs, sizes
+
+
+class Workload:
+    """One compressed batch resident in HBM + everything a decode launch needs."""
+
+    def __init__(self, kind, dataset, n, seed_offset=0, data=None, comp_chunks=None):
+        import torch
+        from nvcomp_b200.batched import Batch, Codec, empty_batch
+        self.kind, self.dataset, self.n = kind, dataset, n
+        self.data = gen_data(dataset, n, seed_offset) if data is None else data
+        self.inp = device_batch(self.data)
+        self.codec = Codec(FMT[kind], opts=codec_opts(kind, dataset))
+        if comp_chunks is None:
+            strided = self.codec.compress(self.inp, max_chunk=CHUNK)
+            torch.cuda.synchronize()
+            self.dense, self.c_offs, self.c_sizes = compact(strided)
+            del strided
+        else:
+            self.dense, self.c_offs, self.c_sizes = host_slab_to_batch(comp_chunks)
+        dev = self.dense.device
+        self.comp = Batch(self.dense, torch.from_numpy(self.c_offs + self.dense.data_ptr()).cuda(),
+                          torch.from_numpy(self.c_sizes).cuda(), self.c_offs)
+        self.comp_total = int(self.c_sizes.sum())
+        self.comp_span = int(self.c_offs[-1] + self.c_sizes[-1])
+        self.total = n * CHUNK
+        self.out = empty_batch(n, CHUNK)
+        self.tb = self.codec.decompress_get_temp_size(n, CHUNK)
+        self.temp = torch.empty(max(self.tb, 1), dtype=torch.uint8, device=dev)
+        self.actual = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.status = torch.full((n,), -1, dtype=torch.int32, device=dev)
+
+    def launch(self, stream_handle, ptrs=None, a=0, b=None, temp=None):
+        b = self.n if b is None else b
+        ptrs = self.comp.ptrs if ptrs is None else ptrs
+        temp = self.temp if temp is None else temp
+        self.codec.decompress_async(ptrs.data_ptr() + 8 * a, self.comp.sizes.data_ptr() + 8 * a,
+                                    self.inp.sizes.data_ptr() + 8 * a, self.actual.data_ptr() + 8 * a, b - a,
+                                    temp.data_ptr(), self.tb, self.out.ptrs.data_ptr() + 8 * a,
+                                    self.status.data_ptr() + 4 * a, stream_handle)
+
+    def check(self):
+        import torch
+        torch.cuda.synchronize()
+        assert bool((self.status == 0).all().item()) and bool((self.actual == CHUNK).all().item()), "decompress status/size"
+        assert torch.equal(self.out.slab[: self.total], self.inp.slab[: self.total]), "decompressed bytes differ from the input"
+
+    def reset_outputs(self):
+        self.out.slab.zero_(); self.status.fill_(-1); self.actual.zero_()
+
+    def alg_bytes(self):
+        return self.total + self.comp_total + 44 * self.n
+
+
+def time_decode(w: Workload, steps: int, warmup: int):
+    """CUDA events on the launching stream around every launch and around the whole timed region."""
+    import torch
+    sh = torch.cuda.current_stream().cuda_stream
+    for _ in range(max(warmup, 3)):
+        w.launch(sh)
+    w.check()                       # parity gate before timing: bit-exact vs the original data, every status success
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for a, b in evs:
+        a.record()
+        w.launch(sh)
+        b.record()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, [a.elapsed_time(b) for a, b in evs]
+
+
+def rate_line(w: Workload, ms: float, peak: float):
+    return {"chunks": w.n, "ratio": round(w.total / w.comp_total, 3), "GBps": round(w.total / ms / 1e6, 1),
+            "ms": round(ms, 4), "roofline_frac": round(w.alg_bytes() / ms / 1e6 / peak, 4)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the multi-GPU job: rank 0 owns every rank's compressed slab and scatters it while the ranks decode
+# ----------------------------------------------------------------------------------------------
+class DistributedJob:
+    NSLICES = 4
+
+    def __init__(self, w: Workload, rank: int, world: int):
+        import torch
+        import torch.distributed as dist
+        self.w, self.rank, self.world = w, rank, world
+        dev = w.dense.device
+        n = w.n
+        self.bounds = [n * i // self.NSLICES for i in range(self.NSLICES + 1)]
+        self.spans = [(int(w.c_offs[a]), int(w.c_offs[b - 1] + w.c_sizes[b - 1])) for a, b in zip(self.bounds, self.bounds[1:])]
+        # setup (untimed): rank 0 collects every rank's compressed slab + slice table -- "rank 0 owns the input"
+        meta = torch.tensor([w.comp_span] + [x for s in self.spans for x in s], dtype=torch.int64, device=dev)
+        metas = [torch.zeros_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        self.metas = [m.cpu().tolist() for m in metas]
+        self.owned = {}
+        if rank == 0:
+            for r in range(1, world):
+                self.owned[r] = torch.empty(self.metas[r][0], dtype=torch.uint8, device=dev)
+                dist.recv(self.owned[r], r)
+        else:
+            dist.send(w.dense[: w.comp_span].contiguous(), 0)
+            self.recv_buf = torch.zeros(w.comp_span + 64, dtype=torch.uint8, device=dev)
+            self.recv_ptrs = torch.from_numpy(w.c_offs + self.recv_buf.data_ptr()).to(dev)
+        self.comm = torch.cuda.Stream()
+        self.temps = [torch.empty(max(w.tb, 1), dtype=torch.uint8, device=dev) for _ in range(self.NSLICES)]
+        self.dist = dist
+        self.torch = torch
+
+    def step(self, decode=True):
+        """One job: every slice of every remote rank's share leaves rank 0 on the comm stream; a rank decodes slice i
+        as soon as it has arrived (rank 0 decodes its own share from the slab it already holds)."""
+        torch, dist, w = self.torch, self.dist, self.w
+        cur = torch.cuda.current_stream()
+        self.comm.wait_stream(cur)                       # the previous job's decode has consumed the buffers
+        works = []
+        with torch.cuda.stream(self.comm):
+            for i in range(self.NSLICES):
+                if self.rank == 0:
+                    ops = []
+                    for r in range(1, self.world):
+                        lo, hi = self.metas[r][1 + 2 * i], self.metas[r][2 + 2 * i]
+                        ops.append(dist.P2POp(dist.isend, self.owned[r][lo:hi], r))
+                    works.append(dist.batch_isend_irecv(ops) if ops else [])
+                else:
+                    lo, hi = self.spans[i]
+                    works.append(dist.batch_isend_irecv([dist.P2POp(dist.irecv, self.recv_buf[lo:hi], 0)]))
+        for i in range(self.NSLICES):
+            a, b = self.bounds[i], self.bounds[i + 1]
+            if self.rank != 0:
+                for wk in works[i]:
+                    wk.wait()                            # the current (decode) stream waits for this slice only
+            if decode:
+                w.launch(cur.cuda_stream, ptrs=None if self.rank == 0 else self.recv_ptrs, a=a, b=b, temp=self.temps[i])
+        if self.rank == 0:
+            for ws in works:
+                for wk in ws:
+                    wk.wait()
+
+    def timed(self, steps, warmup, decode=True):
+        torch, dist = self.torch, self.dist
+        for _ in range(max(warmup, 3)):
+            self.step(decode)
+        torch.cuda.synchronize()
+        if decode:
+            self.w.check()
+            if self.rank != 0:
+                assert torch.equal(self.recv_buf[: self.w.comp_span], self.w.dense[: self.w.comp_span]), "scattered slab differs"
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step(decode)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=self.w.dense.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(kind, dataset, n, rank, world, args, sampler=None):
+    """Decode-only timing (every N) and, for N > 1, the distribution-inclusive job."""
+    import torch
+    import torch.distributed as dist
+    w = Workload(kind, dataset, n, seed_offset=rank)
+    dev = w.dense.device
+    if sampler is not None:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    ms_dec, launch_ms = time_decode(w, args.steps, args.warmup)
+    res = {"w": w, "launch_ms": launch_ms}
+    if world > 1:
+        t = torch.tensor([ms_dec], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dec = float(t.item())
+        cs = torch.tensor([float(w.comp_total)], device=dev)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+        res["comp_total_all"] = float(cs.item())
+        w.reset_outputs()
+        job = DistributedJob(w, rank, world)
+        ms_job = job.timed(args.steps, args.warmup, decode=True)
+        ms_comm = job.timed(max(3, args.steps // 2), 3, decode=False)
+        sent = res["comp_total_all"] - w.comp_total if rank == 0 else 0.0
+        st = torch.tensor([sent], device=dev)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        res.update({"ms_job": ms_job, "ms_comm": ms_comm, "bytes_sent_by_rank0": float(st.item())})
+    else:
+        res["comp_total_all"] = float(w.comp_total)
+    res["ms_dec"] = ms_dec
+    return res
+
+
+def foreign_streams(kind, base: Workload, args, peak):
+    """The same chunks compressed on the HOST by an independent codec, decoded on the GPU (bit-exact gate)."""
+    from concurrent.futures import ThreadPoolExecutor
+    out = {}
+    producers = []
+    n = base.n
+    if kind == "snappy":
+        import pyarrow as pa
+        codec = pa.Codec("snappy")
+        producers.append(("pyarrow_snappy", n, lambda raw: codec.compress(raw).to_pybytes()))
+    elif kind == "lz4":
+        lz4 = C.CDLL("liblz4.so.1")
+        lz4.LZ4_compress_default.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        lz4.LZ4_compress_HC.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        cap = CHUNK + CHUNK // 255 + 64
+
+        def lz4_default(raw):
+            buf = C.create_string_buffer(cap)
+            return buf.raw[: lz4.LZ4_compress_default(raw, buf, len(raw), cap)]
+
+        def lz4_hc(raw):
+            buf = C.create_string_buffer(cap)
+            return buf.raw[: lz4.LZ4_compress_HC(raw, buf, len(raw), cap, 12)]
+        producers.append(("liblz4_default", n, lz4_default))
+        producers.append(("liblz4_hc12", min(n, 4000), lz4_hc))     # HC-12 is slow to produce: bounded sample, stated
+    for name, m, fn in producers:
+        data = base.data[:m]
+        with ThreadPoolExecutor(max_workers=min(64, os.cpu_count() or 1)) as ex:
+            chunks = list(ex.map(lambda i: fn(data[i].tobytes()), range(m)))
+        w = Workload(kind, base.dataset, m, data=data, comp_chunks=chunks)
+        ms, _ = time_decode(w, max(5, args.steps // 2), 3)
+        out[name] = rate_line(w, ms, peak)
+        del w
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from nvcomp_b200.batched import Batch, empty_batch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = pin_to_gpu_numa(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         torch.cuda.set_device(0)
-    dev = torch.device("cuda", torch.cuda.current_device())
 
     kind = args.codec
     dataset = args.dataset or DEFAULT_DATASET[kind]
     n = args.chunks
-    data, inp, codec, comp_strided = build_workload(kind, dataset, n, rank)
-    dense, c_offs, c_sizes = compact(comp_strided)
-    del comp_strided
-    comp = Batch(dense, torch.from_numpy(c_offs + dense.data_ptr()).cuda(), torch.from_numpy(c_sizes).cuda(), c_offs)
-    comp_total = int(c_sizes.sum())
-    total = n * CHUNK
-
-    # ---- optional NCCL distribution step (north_star: rank 0 broadcasts the compressed slab + the
-    # (offset, size) table, every rank decodes its own chunk range).  Measured, not part of `value`.
-    distribute = None
-    if world > 1:
-        from nvcomp_b200 import shard
-        distribute = shard.exchange_demo(dense, c_offs, c_sizes, rank, world)
-
-    out = empty_batch(n, CHUNK)
-    caps = inp.sizes
-    tb = codec.decompress_get_temp_size(n, CHUNK)
-    temp = torch.empty(max(tb, 1), dtype=torch.uint8, device=dev)
-    actual = torch.zeros(n, dtype=torch.int64, device=dev)
-    status = torch.full((n,), -1, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
-    sh = stream.cuda_stream
-
-    def step():
-        codec.decompress_async(comp.ptrs.data_ptr(), comp.sizes.data_ptr(), caps.data_ptr(), actual.data_ptr(), n,
-                               temp.data_ptr(), tb, out.ptrs.data_ptr(), status.data_ptr(), sh)
-
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()          # sampled from the warm-up on: same kernel, same load as the timed region
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    # parity gate before timing: bit-exact vs the original data, every status success
-    assert bool((status == 0).all().item()) and bool((actual == CHUNK).all().item()), "decompress status/size"
-    assert torch.equal(out.slab[:total], inp.slab[:total]), "decompressed bytes differ from the input"
-
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for a, b in evs:
-        a.record()
-        step()
-        b.record()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    launch_ms = [a.elapsed_time(b) for a, b in evs]
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        cs = torch.tensor([float(comp_total)], device=dev)
-        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
-        comp_total_all = float(cs.item())
-    else:
-        comp_total_all = float(comp_total)
+    peak, peak_src = peaks()
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    m = measure(kind, dataset, n, rank, world, args, sampler)
+    w = m["w"]
     if rank == 0:
         # the timed region lasts only tens of ms; keep the identical load running (untimed) until the
         # sampler has seen ~0.6 s of it, so the clock record describes this kernel under load
+        sh = torch.cuda.current_stream().cuda_stream
         t_load = time.time()
         while time.time() - t_load < 0.6:
             for _ in range(10):
-                step()
+                w.launch(sh)
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + 0.6 s of the same launches (untimed), nvidia-smi -lms 20"
 
     # ---- e2e: host buffers in, host buffers out, through the same C-ABI call, pipelined in slices
-    e2e = run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world)
-    e2e_dev = run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world, copy_back=False)
+    e2e = run_e2e(w, args, world)
+    e2e_dev = run_e2e(w, args, world, copy_back=False)
 
-    ms_per_step = elapsed_ms / args.steps
-    value = world * total / (ms_per_step * 1e-3) / 1e9
-    peak, peak_src = peaks()
-    avg_launch_ms = float(np.mean(launch_ms))
-    alg_bytes = total + comp_total + 44 * n
+    total = w.total
+    ms_dec = m["ms_dec"]
+    decode_only = world * total / (ms_dec * 1e-3) / 1e9
+    if world > 1:
+        ms_per_step = m["ms_job"]
+        value = world * total / (ms_per_step * 1e-3) / 1e9
+    else:
+        ms_per_step, value = ms_dec, decode_only
+    avg_launch_ms = float(np.mean(m["launch_ms"]))
+    alg_bytes = w.alg_bytes()
     achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"{kind}:{dataset}")
+        tj = json.load(open(tp))
+        traffic = tj.get(f"{kind}:{dataset}")
+        traffic_src = tj.get("_source", "profiles/traffic.json")
 
     line = {
         "metric": "decompressed GB/s (64KB chunks), whole job",
@@ -311,59 +555,98 @@ def run_gpu(args):
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME[kind], "codec": kind, "dataset": dataset, "chunks_per_gpu": n,
-                   "chunk_bytes": CHUNK, "compression_ratio": round(world * total / comp_total_all, 3),
+                   "chunk_bytes": CHUNK, "compression_ratio": round(world * total / m["comp_total_all"], 3),
                    "l2_policy": "inputs larger than L2 (compressed + decompressed footprint per step = "
-                                f"{(total + comp_total) / 1e6:.0f} MB vs 126 MB L2)",
-                   "sharding": "contiguous chunk range per rank, no data-path collective" if world > 1 else "single GPU"},
+                                f"{(total + w.comp_total) / 1e6:.0f} MB vs 126 MB L2)",
+                   "sharding": ("contiguous chunk range per rank; rank 0 owns the compressed slab of every range and scatters "
+                                f"it over NCCL in {DistributedJob.NSLICES} slices per rank, overlapped with the decode of the "
+                                "slices that have arrived (inside `value`)") if world > 1 else "single GPU",
+                   "host_placement": numa},
+        "decode_only": {"value": round(decode_only, 2), "unit": "GB/s", "ms_per_step": round(ms_dec, 4),
+                        "what": "the decode launches alone, inputs resident (no distribution), max over ranks"},
         "e2e": e2e,
         "e2e_device_consumer": e2e_dev,
-        "gpu_launches": args.steps,
+        "gpu_launches": 2 * args.steps if kind in ("lz4", "snappy") else args.steps,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "frac": round(achieved / peak, 4), "traffic": traffic,
+                     "traffic_source": traffic_src or "not captured for this workload",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": KERNEL_NAME[kind], "avg_launch_ms": round(avg_launch_ms, 4)},
         "clocks": clocks,
     }
-    if distribute is not None:
-        line["distribute"] = distribute
-    if rank == 0 and world == 1 and not args.no_cpu:
-        sample = min(n, args.cpu_chunks)
-        host = dense[: int(c_offs[sample - 1] + c_sizes[sample - 1])].cpu().numpy() if sample else np.zeros(1, np.uint8)
-        line["cpu_baseline"] = cpu_baseline(kind, host, c_offs[:sample], c_sizes[:sample], data[:sample])
+    if world > 1:
+        line["distribute"] = {
+            "what": "the job's NCCL scatter alone (no decode), warm, max over ranks: bytes leaving rank 0 per step / time",
+            "bytes": int(m["bytes_sent_by_rank0"]), "ms": round(m["ms_comm"], 3),
+            "GBps": round(m["bytes_sent_by_rank0"] / (m["ms_comm"] * 1e-3) / 1e9, 1)}
+
+    if rank == 0 and world == 1:
+        if kind in ("lz4", "snappy") and not args.no_extras:
+            per = {}
+            for name, ds in (("cfg2_i_gen_data3", "snappy_synth"), ("cfg2_ii_price_walk_f32", "tabular_f32:0")):
+                wd = Workload(kind, ds, n)
+                ms, _ = time_decode(wd, max(5, args.steps // 2), 3)
+                per[name] = rate_line(wd, ms, peak)
+                del wd
+            line["per_dataset"] = per
+            line["foreign_streams"] = foreign_streams(kind, w, args, peak)
+        if not args.no_cpu:
+            sample = min(n, args.cpu_chunks)
+            host = w.dense[: int(w.c_offs[sample - 1] + w.c_sizes[sample - 1])].cpu().numpy()
+            line["cpu_baseline"] = cpu_baseline(kind, host, w.c_offs[:sample], w.c_sizes[:sample], w.data[:sample])
+
+    # ---- BASELINE configs[4]: LZ4, 80,000 x 64 KB in total, strong scaling (N > 1 always; N = 1 with --cfg5)
+    if world > 1 or args.cfg5:
+        m.clear()
+        del w
+        torch.cuda.empty_cache()
+        n5 = CFG5_TOTAL_CHUNKS // world
+        m5 = measure("lz4", "lz4_mixed", n5, rank, world, args)
+        t5 = world * n5 * CHUNK
+        cfg5 = {"workload": "BASELINE configs[4]: LZ4 batched decompress, 80000x64KB chunks (run-length int32 + tabular "
+                            "float32) sharded by contiguous chunk range", "scaling": "strong", "chunks_total": world * n5,
+                "chunks_per_gpu": n5,
+                "decode_only": {"GBps": round(t5 / (m5["ms_dec"] * 1e-3) / 1e9, 2), "ms": round(m5["ms_dec"], 4)}}
+        if world > 1:
+            cfg5["job"] = {"GBps": round(t5 / (m5["ms_job"] * 1e-3) / 1e9, 2), "ms": round(m5["ms_job"], 4),
+                           "what": "rank 0 scatters every other rank's share over NCCL, overlapped with decode"}
+            cfg5["distribute"] = {"bytes": int(m5["bytes_sent_by_rank0"]), "ms": round(m5["ms_comm"], 3),
+                                  "GBps": round(m5["bytes_sent_by_rank0"] / (m5["ms_comm"] * 1e-3) / 1e9, 1)}
+        line["cfg5"] = cfg5
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world, copy_back=True):
+def run_e2e(w: Workload, args, world, copy_back=True):
     """Same decode through the C ABI, but the compressed chunks start in pinned HOST memory and the
     decompressed chunks end in pinned HOST memory; both copies are inside the timed region.  The batch is
-    processed in slices on three streams so H2D, decode and D2H overlap."""
+    processed in slices, one stream per slice (H2D -> decode -> D2H in order on it), so the copies of one
+    slice overlap the decode of another and both copy engines stay busy."""
     import torch
     import torch.distributed as dist
     from nvcomp_b200.batched import empty_batch
-    dev = comp.slab.device
-    total = n * CHUNK
-    comp_total = int(c_offs[-1] + c_sizes[-1])
+    dev = w.dense.device
+    n, total, comp_total = w.n, w.total, w.comp_span
+    c_offs, c_sizes = w.c_offs, w.c_sizes
     h_comp = torch.empty(comp_total, dtype=torch.uint8).pin_memory()
-    h_comp.copy_(comp.slab[:comp_total])
+    h_comp.copy_(w.dense[:comp_total])
     h_out = torch.empty(total, dtype=torch.uint8).pin_memory()
     d_comp = torch.empty(comp_total + 64, dtype=torch.uint8, device=dev)
     out = empty_batch(n, CHUNK)
     ptrs = torch.from_numpy(c_offs + d_comp.data_ptr()).to(dev)
     sizes = torch.from_numpy(c_sizes).to(dev)
-    caps = inp.sizes
+    caps = w.inp.sizes
     actual = torch.zeros(n, dtype=torch.int64, device=dev)
     status = torch.full((n,), -1, dtype=torch.int32, device=dev)
     h_status = torch.empty(n, dtype=torch.int32).pin_memory()
-    nslices = 4
+    nslices = 8
     bounds = [n * i // nslices for i in range(nslices + 1)]
-    # one stream per slice: H2D -> decode -> D2H in order on that stream; the slices' copies share the
-    # two copy engines and their decode kernels overlap (a quarter batch does not fill the GPU)
     streams = [torch.cuda.Stream() for _ in range(nslices)]
-    tb = codec.decompress_get_temp_size(n, CHUNK)
+    tb = w.tb
     temps = [torch.empty(max(tb, 1), dtype=torch.uint8, device=dev) for _ in range(nslices)]
+    codec = w.codec
 
     def step():
         for i in range(nslices):
@@ -387,12 +670,11 @@ def run_e2e(codec, comp, c_offs, c_sizes, inp, n, args, world, copy_back=True):
         step()
     torch.cuda.synchronize()
     ok = bool((h_status == 0).all().item()) and (not copy_back or np.array_equal(
-        h_out.numpy()[: 4 * CHUNK], inp.slab[: 4 * CHUNK].cpu().numpy()))
+        h_out.numpy()[: 4 * CHUNK], w.inp.slab[: 4 * CHUNK].cpu().numpy()))
     assert ok, "e2e output mismatch"
     if world > 1:
         dist.barrier()
     steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -457,9 +739,10 @@ def oracle_compress_batch(lib, kind, dataset, data: np.ndarray):
 def run_reference(args):
     """--impl reference: the reference's own implementation of this path is the closed libnvcomp.so
     (not in /root/reference, not installable: no source, no wheel).  Per the task's tier rules this arm
-    times the CPU implementation of the path instead: the oracle port (oracle/*.c) on all host cores,
-    on a bounded sample of the same workload.  Nothing of libnvcomp.so is loaded on this arm: the synthetic
-    chunks are compressed by the oracle's own CPU encoders and decoded by its decoders."""
+    times the CPU implementation of the path instead, on all host cores, on the same workload: for LZ4 the decoder
+    the reference itself links for its known-answer tests (liblz4's LZ4_decompress_safe, dlopen'd), for the other
+    codecs the oracle port (oracle/*.c).  Nothing of libnvcomp.so is loaded on this arm: the synthetic chunks are
+    compressed by the oracle's own CPU encoders."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
@@ -467,33 +750,29 @@ def run_reference(args):
     kind = args.codec
     dataset = args.dataset or DEFAULT_DATASET[kind]
     n = min(args.chunks, args.cpu_chunks)
-    from nvcomp_b200 import datagen
-    data = datagen.DATASETS[dataset](n)
+    data = gen_data(dataset, n)
     lib = load_oracle()
     host, c_offs, c_sizes = oracle_compress_batch(lib, kind, dataset, data)
     threads = os.cpu_count() or 1
-    offs = np.ascontiguousarray(c_offs, dtype=np.uint64)
-    lens = np.ascontiguousarray(c_sizes, dtype=np.uint64)
-    out_host = np.empty(n * CHUNK, dtype=np.uint8)
-    for _ in range(max(args.warmup, 1)):
-        cpu_decode_time(lib, kind, host, offs, lens, out_host, threads)
-    assert np.array_equal(out_host, data.reshape(-1)), "oracle output differs from the original data"
-    times = [cpu_decode_time(lib, kind, host, offs, lens, out_host, threads) for _ in range(args.steps)]
-    sec = float(np.mean(times))
-    v = n * CHUNK / sec / 1e9
+    use_liblz4 = kind == "lz4" and bool(lib.oracle_have_liblz4())
+    st = cpu_time_stats(lib, ORACLE_ID["liblz4"] if use_liblz4 else ORACLE_ID[kind], host, c_offs, c_sizes, data, threads,
+                        steps=max(args.steps, 3))
+    v = st["median_GBps"]
+    decoder = ("liblz4.so.1 LZ4_decompress_safe (dlopen)" if use_liblz4 else "oracle/ C decoder")
     sample = (f"{n} chunks x 64 KB per step ({'same batch size' if n == args.chunks else 'bounded sample'} as the GPU arm's "
-              f"workload, same generator), oracle/ C encoders + decoders, {threads} pthreads, mean of {args.steps} steps")
+              f"workload, same generator), oracle/ C encoders, {decoder}, {threads} pthreads, median of {st['reps']} steps")
     line = {
         "impl": "reference", "metric": "decompressed GB/s (64KB chunks), whole job", "value": round(v, 2),
-        "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
-        "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "unit": "GB/s", "n_gpus": world, "steps": st["reps"], "warmup": 1,
+        "ms_per_step": round(st["median_s"] * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME[kind], "codec": kind, "dataset": dataset, "chunks_per_step": n,
+        "config": {"workload": WORKLOAD_NAME[kind], "codec": kind, "dataset": dataset, "chunks_per_gpu": n,
                    "chunk_bytes": CHUNK, "compression_ratio": round(n * CHUNK / float(c_sizes.sum()), 3),
                    "note": "the reference library is closed-source and absent; CPU implementation of the path "
-                           "(oracle port) on the host cores, per the task's reference-arm rule"},
-        "cpu_baseline": {"value": round(v, 2), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
-                         "best_GBps": round(n * CHUNK / min(times) / 1e9, 2)},
+                           "on the host cores, per the task's reference-arm rule"},
+        "cpu_baseline": {"value": round(v, 2), "unit": "GB/s", "cores": threads, "kind": "reference" if use_liblz4 else "port",
+                         "sample": sample, "best_GBps": round(st["best_GBps"], 2),
+                         "estimator": "median of the steps (best beside it); the same estimator as the GPU arm's cpu_baseline"},
         "e2e": {"value": round(v, 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -511,6 +790,8 @@ def main():
     ap.add_argument("--chunks", type=int, default=CHUNKS_PER_GPU)
     ap.add_argument("--cpu-chunks", type=int, default=10000, help="bounded CPU sample (chunks)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip per_dataset / foreign_streams (kernel iteration)")
+    ap.add_argument("--cfg5", action="store_true", help="also run BASELINE configs[4] (80,000 LZ4 chunks) at N = 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

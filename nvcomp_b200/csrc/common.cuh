@@ -199,6 +199,48 @@ __device__ __forceinline__ void warp_match_copy(uint8_t* dst, uint32_t off, uint
   }
 }
 
+// ---------------------------------------------------------------------------
+// Run-length expansion from a register window (the direct LZ4 / Snappy loops): a match whose period `off` (1, 2, 4 or
+// 8 bytes) lies in bytes the warp already holds -- byte k of the run is window byte `b` of lane first_lane + (k mod
+// off) -- is written without reading the output back: the 8-byte period is rotated to the destination alignment
+// and broadcast with 16-byte stores.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void lz_expand_period_from_window(uint8_t* dst, uint32_t ml, uint32_t off, uint32_t b,
+                                                             uint32_t first_lane, uint32_t ul) {
+  // 8-byte period P: byte k = window lane first_lane + (k mod off)
+  const uint32_t pb = __shfl_sync(kFull, b, (int)(first_lane + (ul & (off - 1u))));
+  const uint32_t placed = pb << (8u * (ul & 3u));
+  const uint32_t plo = __reduce_or_sync(kFull, ul < 4u ? placed : 0u);
+  const uint32_t phi = __reduce_or_sync(kFull, (ul & 28u) == 4u ? placed : 0u);
+  // every 16-byte aligned vector of the run holds P rotated by (-dst) & 7 bytes, twice
+  const uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+  const uint32_t r0 = head & 7u;
+  const uint32_t wa = (r0 & 4u) ? phi : plo, wb = (r0 & 4u) ? plo : phi, sh = 8u * (r0 & 3u);
+  uint4 v;
+  v.x = __funnelshift_r(wa, wb, sh);
+  v.y = __funnelshift_r(wb, wa, sh);
+  v.z = v.x; v.w = v.y;
+  // byte j of the run, for lanes that write single bytes (j mod 8 selects a byte of P)
+  const uint32_t mine = (((ul & 4u) ? phi : plo) >> (8u * (ul & 3u))) & 0xffu;   // P[lane & 7]
+  if (ml < 16u + head) {
+    // short: bytes only (ml < 31)
+    if (ul < ml) dst[ul] = (uint8_t)mine;
+  } else {
+    if (ul < head) dst[ul] = (uint8_t)mine;
+    const uint32_t nvec = (ml - head) >> 4;
+    uint4* d16 = (uint4*)(dst + head);
+    // nvec <= 64 for matches up to ~1 KB: two predicated stores, a loop only beyond that
+    if (ul < nvec) st_v4(d16 + ul, v);
+    if (ul + kWarp < nvec) st_v4(d16 + ul + kWarp, v);
+#pragma unroll 1
+    for (uint32_t k = ul + 2u * kWarp; k < nvec; k += kWarp) st_v4(d16 + k, v);
+    // ragged end (< 16 bytes): position head + 16 nvec + lane; 16 nvec = 0 mod 8
+    const uint32_t j = head + (nvec << 4) + ul;
+    const uint32_t jb = (((j & 4u) ? phi : plo) >> (8u * (j & 3u))) & 0xffu;
+    if (j < ml) dst[j] = (uint8_t)jb;
+  }
+}
+
 // Host-side launch helper: number of CTAs for a persistent kernel.
 inline int persistent_grid(int ctas_per_sm, size_t work_items, int work_per_cta) {
   size_t need = (work_items + (size_t)work_per_cta - 1) / (size_t)work_per_cta;
@@ -211,16 +253,50 @@ inline int persistent_grid(int ctas_per_sm, size_t work_items, int work_per_cta)
 // "already set" memo is a per-device bitmask, updated atomically: safe from several host threads and for
 // one process driving several GPUs (reference benchmarks/benchmark_allgather.cpp:359-368 pattern).
 template <class Kernel>
-inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>& memo) {
+inline cudaError_t ensure_func_attribute(Kernel kernel, cudaFuncAttribute attr, int value,
+                                         std::atomic<unsigned long long>& memo) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   const bool tracked = dev >= 0 && dev < 64;
   if (tracked && ((memo.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  e = cudaFuncSetAttribute(kernel, attr, value);
   if (e == cudaSuccess && tracked) memo.fetch_or(1ull << dev, std::memory_order_release);
   return e;
 }
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>& memo) {
+  return ensure_func_attribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes, memo);
+}
+
+// Fork / join around a second kernel that should run concurrently with work on the caller's stream (the light and
+// the dense LZ decode kernels of one batch: as the dense kernel's persistent CTAs drain, CTAs of the light kernel
+// take their place instead of leaving the tail of the batch to a few busy SMs).  The side stream is per device and
+// lives for the process; the two events are per call (recorded once, destroyed right away: CUDA releases them when
+// they complete), so concurrent callers on different streams never share an event.  Works under stream capture.
+cudaError_t side_stream_for_current_device(cudaStream_t* side);
+struct StreamFork {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  cudaError_t begin(cudaStream_t stream) {
+    main = stream;
+    cudaError_t e = side_stream_for_current_device(&side);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(fork_ev, main)) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(side, fork_ev, 0);
+  }
+  cudaError_t end() {
+    cudaError_t e = cudaEventRecord(join_ev, side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main, join_ev, 0);
+    return e;
+  }
+  ~StreamFork() {
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    if (join_ev) cudaEventDestroy(join_ev);
+  }
+};
 
 // call logging (log.cu): NVCOMP_LOG_LEVEL >= 3 logs every low-level API call
 int log_level();

@@ -52,3 +52,24 @@ void log_call(const char* fn, size_t batch, size_t max_chunk, const void* stream
 }
 
 }  // namespace b200
+
+namespace b200 {
+
+// one non-blocking side stream per device, created on first use and kept for the process (see StreamFork)
+cudaError_t side_stream_for_current_device(cudaStream_t* side) {
+  static std::mutex mu;
+  static cudaStream_t streams[64] = {nullptr};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!streams[dev]) {
+    e = cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+  }
+  *side = streams[dev];
+  return cudaSuccess;
+}
+
+}  // namespace b200

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "lz77_compress.cuh"
 #include "lz4_decode.cuh"
+#include "lz_sched.cuh"
 #include "nvcomp/lz4.h"
 
 namespace b200 {
@@ -41,15 +42,6 @@ constexpr int kLzDecCtasPerSm = 7;
 // light kernel: no shared memory, 10 CTAs x 4 warps per SM (long copies want many warps in flight)
 constexpr int kLzLightCtasPerSm = 10;
 
-// A batch is decoded by two kernels.  "Light" chunks -- compressed >= 4x (long matches, typed run-length data) or
-// practically incompressible (one long literal run) -- are streamed by the direct global-memory sequence loop,
-// which needs no shared memory and runs at high occupancy.  Everything else is dense short-token data and goes
-// to the block-parallel decoder (lz_decode.cuh).  Both kernels walk the whole batch with their own ticket counter
-// and skip the other kernel's chunks.
-__device__ __forceinline__ bool lz_chunk_is_light(uint64_t cap, uint64_t in_n) {
-  return cap >= 4ull * in_n || in_n + (cap >> 6) >= cap;
-}
-
 __global__ void __launch_bounds__(kLzDecWarps * 32, kLzLightCtasPerSm)
 lz4_decompress_light_kernel(const void* const* __restrict__ comp_ptrs,
                             const size_t* __restrict__ comp_bytes,
@@ -57,15 +49,14 @@ lz4_decompress_light_kernel(const void* const* __restrict__ comp_ptrs,
                             size_t* actual_bytes, size_t batch,
                             void* const* __restrict__ out_ptrs,
                             nvcompStatus_t* statuses,
-                            unsigned long long* ticket) {
+                            LzLists lists) {
   const int lane = lane_id();
   const size_t warp_global = (size_t)blockIdx.x * kLzDecWarps + (threadIdx.x >> 5);
   const size_t warps_total = (size_t)gridDim.x * kLzDecWarps;
-  WarpTicket sched(ticket, warp_global, warps_total);
+  LzWork sched(lists, true, comp_bytes, out_caps, batch, warp_global, warps_total);
   for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
     const size_t in_n64 = comp_bytes[c];
     const uint64_t cap = (uint64_t)out_caps[c];
-    if (!lz_chunk_is_light(cap, in_n64)) continue;
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
     __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
@@ -87,23 +78,24 @@ lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
                          size_t* actual_bytes, size_t batch,
                          void* const* __restrict__ out_ptrs,
                          nvcompStatus_t* statuses,
-                         unsigned long long* ticket) {
+                         LzLists lists) {
   __shared__ __align__(16) uint8_t s_ring[kLzDecWarps][kLzWarpSmem];
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
   const size_t warp_global = (size_t)blockIdx.x * kLzDecWarps + w;
   const size_t warps_total = (size_t)gridDim.x * kLzDecWarps;
-  WarpTicket sched(ticket, warp_global, warps_total);
+  lz_warp_init(smem_addr(s_ring[w]), lane);
+  uint32_t tma_parity = 0;
+  LzWork sched(lists, false, comp_bytes, out_caps, batch, warp_global, warps_total);
   for (size_t c = sched.next(lane); c < batch; c = sched.next(lane)) {
     const size_t in_n64 = comp_bytes[c];
     const uint64_t cap = (uint64_t)out_caps[c];
-    if (lz_chunk_is_light(cap, in_n64)) continue;
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
     __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
     uint32_t produced = 0;
     bool ok = in_n64 <= 0xffffffffull;
-    if (ok) ok = lz4_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], lane, false);
+    if (ok) ok = lz4_decode_chunk_v2(in, (uint32_t)in_n64, out, cap, &produced, s_ring[w], tma_parity, lane, false);
     if (lane == 0) {
       if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
       if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
@@ -236,9 +228,9 @@ nvcompStatus_t nvcompBatchedLZ4CompressAsync(
 }
 
 nvcompStatus_t nvcompBatchedLZ4DecompressGetTempSize(
-    size_t, size_t, size_t* temp_bytes) {
+    size_t batch, size_t, size_t* temp_bytes) {
   if (!temp_bytes) return nvcompErrorInvalidValue;
-  *temp_bytes = kSchedBytes;
+  *temp_bytes = lz_decode_temp_bytes(batch);     // ticket counters + the two chunk-index lists (lz_sched.cuh)
   return nvcompSuccess;
 }
 
@@ -266,17 +258,27 @@ nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
   log_call("nvcompBatchedLZ4DecompressAsync", batch, 0, stream);
   if (batch == 0) return nvcompSuccess;
   if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
-  unsigned long long* ticket = nullptr;
-  if (temp && temp_bytes >= kSchedBytes) {
-    ticket = (unsigned long long*)temp;
-    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned long long), stream));
+  const LzLists lists = lz_lists_in(temp, temp_bytes, batch);
+  if (lists.ctr) {
+    B200_CUDA_TRY(cudaMemsetAsync(lists.ctr, 0, 4 * sizeof(unsigned long long), stream));
+    lz_classify_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, stream>>>(comp_bytes, out_caps, batch, lists);
   }
-  const int grid_l = persistent_grid(kLzLightCtasPerSm, batch, kLzDecWarps);
-  lz4_decompress_light_kernel<<<grid_l, kLzDecWarps * 32, 0, stream>>>(
-      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket);
+  // dense kernel on the caller's stream, light kernel beside it (see StreamFork): both are ordered after the ticket
+  // reset above and before anything the caller enqueues next
+  StreamFork fork;
+  B200_CUDA_TRY(fork.begin(stream));
   const int grid = persistent_grid(kLzDecCtasPerSm, batch, kLzDecWarps);
   lz4_decompress_v2_kernel<<<grid, kLzDecWarps * 32, 0, stream>>>(
-      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, ticket ? ticket + 1 : nullptr);
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, lists);
+  // both kernels ask for the same shared-memory carveout: an SM does not have to drain and reconfigure between a dense
+  // CTA leaving and a light CTA arriving (or between back-to-back calls)
+  static std::atomic<unsigned long long> carveout_set{0};
+  B200_CUDA_TRY(ensure_func_attribute(lz4_decompress_light_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared, carveout_set));
+  const int grid_l = persistent_grid(kLzLightCtasPerSm, batch, kLzDecWarps);
+  lz4_decompress_light_kernel<<<grid_l, kLzDecWarps * 32, 0, fork.side>>>(
+      comp_ptrs, comp_bytes, out_caps, actual_bytes, batch, out_ptrs, statuses, lists);
+  B200_CUDA_TRY(fork.end());
   B200_CUDA_TRY(cudaGetLastError());
   return nvcompSuccess;
 }

@@ -108,38 +108,7 @@ __device__ __forceinline__ bool lz4_decode_chunk_direct(const uint8_t* __restric
             continue;
           }
           // period (1, 2, 4 or 8 bytes) inside this sequence's literals: expand from the window
-          // 8-byte period P: byte k = literal[ll - off + (k mod off)] = window lane 1 + ll - off + (k mod off)
-          const uint32_t pb = __shfl_sync(kFull, b, 1u + ll - off + (ul & (off - 1u)));
-          const uint32_t placed = pb << (8u * (ul & 3u));
-          const uint32_t plo = __reduce_or_sync(kFull, ul < 4u ? placed : 0u);
-          const uint32_t phi = __reduce_or_sync(kFull, (ul & 28u) == 4u ? placed : 0u);
-          // every 16-byte aligned vector of the run holds P rotated by (-dst) & 7 bytes, twice
-          const uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
-          const uint32_t r0 = head & 7u;
-          const uint32_t wa = (r0 & 4u) ? phi : plo, wb = (r0 & 4u) ? plo : phi, sh = 8u * (r0 & 3u);
-          uint4 v;
-          v.x = __funnelshift_r(wa, wb, sh);
-          v.y = __funnelshift_r(wb, wa, sh);
-          v.z = v.x; v.w = v.y;
-          // byte j of the run, for lanes that write single bytes (j mod 8 selects a byte of P)
-          const uint32_t mine = (((ul & 4u) ? phi : plo) >> (8u * (ul & 3u))) & 0xffu;   // P[lane & 7]
-          if (ml < 16u + head) {
-            // short: bytes only (ml < 31)
-            if (ul < ml) dst[ul] = (uint8_t)mine;
-          } else {
-            if (ul < head) dst[ul] = (uint8_t)mine;
-            const uint32_t nvec = (ml - head) >> 4;
-            uint4* d16 = (uint4*)(dst + head);
-            // nvec <= 64 for matches up to ~1 KB: two predicated stores, a loop only beyond that
-            if (ul < nvec) st_v4(d16 + ul, v);
-            if (ul + kWarp < nvec) st_v4(d16 + ul + kWarp, v);
-#pragma unroll 1
-            for (uint32_t k = ul + 2u * kWarp; k < nvec; k += kWarp) st_v4(d16 + k, v);
-            // ragged end (< 16 bytes): position head + 16 nvec + lane; 16 nvec = 0 mod 8
-            const uint32_t j = head + (nvec << 4) + ul;
-            const uint32_t jb = (((j & 4u) ? phi : plo) >> (8u * (j & 3u))) & 0xffu;
-            if (j < ml) dst[j] = (uint8_t)jb;
-          }
+          lz_expand_period_from_window(dst, ml, off, b, 1u + ll - off, ul);
           op += ll + ml;
           ip += used;
           continue;
@@ -211,7 +180,7 @@ struct Lz4Decode : Lz4Policy {
 
 __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t in_n, uint8_t* out,
                                                     uint64_t out_cap, uint32_t* produced,
-                                                    uint8_t* ring, int lane, bool allow_direct = true) {
+                                                    uint8_t* ring, uint32_t& tma_parity, int lane, bool allow_direct = true) {
   if (in_n == 0) { *produced = 0; return true; }
   // Adaptive strategy: a chunk that compressed >= 4x is dominated by long matches; the ring /
   // lane-parallel machinery only costs instructions there, so it is decoded by the direct
@@ -223,7 +192,10 @@ __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t 
   s.ip = 0; s.op = 0; s.flushed = 0; s.ring_lo = 0;
   s.align = (uint32_t)((uintptr_t)out & 15u);
   s.ring = smem_addr(ring);
-  if (!lz_decode_stream<Lz4Decode>(s, lane)) return false;
+  s.cur = 0; s.pf_ip = kNoPrefetch; s.parity = tma_parity;
+  const bool ok = lz_decode_stream<Lz4Decode>(s, lane);
+  tma_parity = s.parity;                 // the barrier outlives the chunk: carry its phase to the next one
+  if (!ok) return false;
   *produced = s.op;
   return true;
 }

@@ -44,7 +44,12 @@ struct LzState {
   uint32_t ring_lo;    // lowest output offset whose bytes are valid in the ring
   uint32_t align;      // (uintptr_t)out & 15: ring index = (offset + align) & mask
   uint32_t ring;       // shared-window address of the kRingBytes ring (32-bit: LDS/STS with immediates)
+  // compressed-input staging (lz_block): two block buffers filled by TMA bulk copies behind one mbarrier
+  uint32_t cur;        // buffer that holds the block being parsed
+  uint32_t pf_ip;      // input position whose block is being prefetched into the other buffer (kNoPrefetch: none)
+  uint32_t parity;     // phase parity the next mbarrier wait uses
 };
+constexpr uint32_t kNoPrefetch = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t ring_idx(const LzState& s, uint32_t off) {
   return (off + s.align) & kRingMask;
@@ -178,12 +183,33 @@ constexpr uint32_t kBlkBytes = 32 * kSegBytes;
 constexpr uint32_t kBlkPad = 32;
 constexpr uint32_t kBlkStage = kBlkBytes + kBlkPad;
 constexpr uint32_t kMaxStepOut = 32 * kMaxTokOut;   // output bytes one step may append (the ring reach depends on it)
-constexpr uint32_t kSmemIn = kRingBytes;            // staged block
-constexpr uint32_t kSmemSz = kSmemIn + kBlkStage;   // token size of every block byte
-constexpr uint32_t kSmemRec = kSmemSz + kBlkBytes;  // exit tables (1 B x 1024), then token positions (2 B x 512)
-constexpr uint32_t kLzWarpSmem = kSmemRec + kBlkBytes;
+constexpr uint32_t kSmemIn = kRingBytes;            // two block buffers: the staged block | its token sizes, then the
+                                                    // next block prefetched over the (dead) sizes; roles swap per block
+constexpr uint32_t kSmemRec = kSmemIn + 2 * kBlkStage;  // exit tables (1 B x 1024), then token positions (2 B x 512)
+constexpr uint32_t kSmemMbar = kSmemRec + kBlkBytes;    // mbarrier of the TMA bulk copies
+constexpr uint32_t kLzWarpSmem = kSmemMbar + 16;
 static_assert(kRingReach + kMaxStepOut + 16 <= kRingBytes, "ring reach");
-static_assert(kSmemSz % 16 == 0 && kSmemRec % 16 == 0, "alignment");
+static_assert(kSmemRec % 16 == 0 && kSmemMbar % 8 == 0 && kBlkStage % 16 == 0, "alignment");
+
+// Called once per warp before its first chunk (the barrier lives as long as the kernel).
+__device__ __forceinline__ void lz_warp_init(uint32_t ring, int lane) {
+  if (lane == 0) mbar_init(ring + kSmemMbar, 1);
+  __syncwarp();
+}
+// wait for the bulk copy in flight (one is in flight whenever this is called)
+__device__ __forceinline__ void lz_stage_wait(LzState& s) {
+  mbar_wait(s.ring + kSmemMbar, s.parity);
+  s.parity ^= 1u;
+}
+// lane 0 starts the bulk copy of `bytes` (multiple of 16) from the 16-byte aligned `src` into block buffer `buf`
+__device__ __forceinline__ void lz_stage_issue(const LzState& s, uint32_t buf, const uint8_t* src, uint32_t bytes, int lane) {
+  __syncwarp();                                     // every lane is done with the buffer (generic proxy) ...
+  if (lane == 0) {
+    fence_proxy_async_smem();                       // ... before the async proxy overwrites it
+    mbar_expect_tx(s.ring + kSmemMbar, bytes);
+    tma_bulk_g2s(s.ring + kSmemIn + kBlkStage * buf, src, bytes, s.ring + kSmemMbar);
+  }
+}
 
 // Returns the number of tokens retired (0: nothing done, the caller takes the serial path), -1 on a
 // malformed stream.
@@ -197,21 +223,21 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
   uint32_t nl = (avail - kBlkPad) / kSegBytes;                // segments that lie (with the pad) inside the stream
   if (nl > 32u) nl = 32u;
   const uint8_t* const abase = ipp - mis;
-  const uint32_t blk = s.ring + kSmemIn, szs = s.ring + kSmemSz, rec = s.ring + kSmemRec;
+  const uint32_t rec = s.ring + kSmemRec;
 
-  // ---- 1. stage ------------------------------------------------------------------------------
+  // ---- 1. stage: TMA bulk copy of the block into shared memory -----------------------------------
+  // The previous call already prefetched this block if its chain ended at a token boundary (below); otherwise
+  // (first block of the chunk, after serial tokens) it is fetched now.  Either way exactly one copy is in flight.
+  if (s.pf_ip != kNoPrefetch && s.pf_ip != s.ip) { lz_stage_wait(s); s.pf_ip = kNoPrefetch; }   // stale prefetch
+  if (s.pf_ip == s.ip) s.cur ^= 1u;
+  else lz_stage_issue(s, s.cur, abase, kSegBytes * nl + kBlkPad, lane);
+  s.pf_ip = kNoPrefetch;
+  lz_stage_wait(s);
+  const uint32_t blk = s.ring + kSmemIn + kBlkStage * s.cur, szs = s.ring + kSmemIn + kBlkStage * (s.cur ^ 1u);
   uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
   if (ul < nl) {
-    a0 = ld_nc_v4((const uint4*)(abase + kSegBytes * ul));
-    a1 = ld_nc_v4((const uint4*)(abase + kSegBytes * ul + 16u));
-  }
-  if (ul < nl) {                                              // (the segment of lane nl is the pad: lanes 0/1 fill it)
-    sts_v4(blk + kSegBytes * ul, a0);
-    sts_v4(blk + kSegBytes * ul + 16u, a1);
-  }
-  if (ul < kBlkPad / 16u) {
-    const uint4 pad = ld_nc_v4((const uint4*)(abase + kSegBytes * nl + 16u * ul));
-    sts_v4(blk + kSegBytes * nl + 16u * ul, pad);
+    a0 = lds_v4(blk + kSegBytes * ul);
+    a1 = lds_v4(blk + kSegBytes * ul + 16u);
   }
   // Per-lane byte arrays (token sizes, exit table) use a lane-private bank layout: byte p of lane l lives in
   // word (p >> 2) * 32 + l, i.e. every lane stays in its own shared-memory bank whatever p it indexes
@@ -276,6 +302,18 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
       sts_u16(ra, kSegBytes * ul + q);
       q += lds_u8(my_sz + lane_private(q));
       ra += 2u;
+    }
+  }
+  // the size bytes are dead: prefetch the next block over them while this one executes (only when this block
+  // ends at a token boundary the block path will continue from)
+  if (stop_lane == 32u) {
+    const uint32_t next_ip = s.ip + end_pos - mis;
+    const uint32_t nmis = (uint32_t)((uintptr_t)(s.in + next_ip) & 15u);
+    const uint32_t navail = s.in_n - next_ip + nmis;
+    if (navail >= kSegBytes + kBlkPad) {
+      const uint32_t nnl = min((navail - kBlkPad) / kSegBytes, 32u);
+      lz_stage_issue(s, s.cur ^ 1u, s.in + next_ip - nmis, kSegBytes * nnl + kBlkPad, lane);
+      s.pf_ip = next_ip;
     }
   }
   __syncwarp();
@@ -582,7 +620,7 @@ __device__ __forceinline__ void lz_emit_match(LzState& s, uint32_t off, uint32_t
 // Decode driver shared by LZ4 and Snappy.  P::serial_token(s, lane) executes exactly one token
 // at s.ip with the emitters above and returns 1 (continue), 2 (stream finished) or -1 (malformed).
 template <class P>
-__device__ __forceinline__ bool lz_decode_stream(LzState& s, int lane) {
+__device__ __forceinline__ bool lz_decode_loop(LzState& s, int lane) {
   while (true) {
     if (P::at_end(s)) break;
     // a token that needs the serial path is recognised from its first byte: do not pay for a
@@ -599,6 +637,13 @@ __device__ __forceinline__ bool lz_decode_stream(LzState& s, int lane) {
   }
   lz_flush(s, s.op, lane);
   return true;
+}
+
+template <class P>
+__device__ __forceinline__ bool lz_decode_stream(LzState& s, int lane) {
+  const bool ok = lz_decode_loop<P>(s, lane);
+  if (s.pf_ip != kNoPrefetch) { lz_stage_wait(s); s.pf_ip = kNoPrefetch; }   // no copy may outlive the chunk
+  return ok;
 }
 
 }  // namespace b200

@@ -25,7 +25,7 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
 // Streaming store: decompressed output is written once, never re-read by this
 // kernel beyond the match window, so do not let it thrash L1.
 __device__ __forceinline__ void st_v4(uint4* p, const uint4& v) {
-  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};"
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint4 ld_v4(const uint4* p) {

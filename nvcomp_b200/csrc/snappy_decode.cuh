@@ -32,7 +32,43 @@ __device__ __forceinline__ bool snappy_decode_chunk(const uint8_t* __restrict__ 
   if (ulen > out_cap) return false;
   const uint32_t n_out = (uint32_t)ulen;
   uint32_t op = 0;
+  const uint32_t ul = (uint32_t)lane;
   while (ip < in_n) {
+    if (ip + 32u <= in_n) {
+      // Window path (typed run-length data: a short literal followed by copies of it).  One coalesced 32-byte load
+      // brings the literal element and the copy elements behind it into a register window; when the copy's period
+      // (1, 2, 4 or 8 bytes) lies inside the literal, the whole run -- every following copy-2 element of the window
+      // with the same offset continues it -- is expanded from the window, no load from the output buffer.
+      const uint32_t b = in[ip + ul];
+      const uint32_t tag = __shfl_sync(kFull, b, 0);
+      if ((tag & 3u) == 0u && (tag >> 2) < 8u) {                 // literal of 1..8 bytes
+        const uint32_t ll = (tag >> 2) + 1u;
+        const uint32_t t2 = __shfl_sync(kFull, b, (int)(1u + ll));
+        const uint32_t k2 = t2 & 3u;
+        const uint32_t o_lo = __shfl_sync(kFull, b, (int)(2u + ll)), o_hi = __shfl_sync(kFull, b, (int)(3u + ll));
+        uint32_t off, ml, used;
+        if (k2 == 1u) { off = ((t2 >> 5) << 8) | o_lo; ml = 4u + ((t2 >> 2) & 7u); used = 3u + ll; }
+        else { off = o_lo | (o_hi << 8); ml = (t2 >> 2) + 1u; used = 4u + ll; }
+        if ((k2 == 1u || k2 == 2u) && off != 0u && off <= ll && off <= 8u && (off & (off - 1u)) == 0u) {
+          // lane i inspects the i-th element behind the first copy
+          const uint32_t p = used + 3u * ul;
+          const uint32_t e0 = __shfl_sync(kFull, b, (int)(p & 31u)), e1 = __shfl_sync(kFull, b, (int)((p + 1u) & 31u)),
+                         e2 = __shfl_sync(kFull, b, (int)((p + 2u) & 31u));
+          const bool same = p + 3u <= 32u && (e0 & 3u) == 2u && (e1 | (e2 << 8)) == off;
+          const unsigned m = __ballot_sync(kFull, same);
+          const uint32_t nf = (uint32_t)__ffs((int)~m) - 1u;     // leading run of continuations (< 10)
+          ml += __reduce_add_sync(kFull, ul < nf ? (e0 >> 2) + 1u : 0u);
+          used += 3u * nf;
+          if (ll <= n_out - op && ml <= n_out - op - ll) {
+            if (ul - 1u < ll) out[op + ul - 1u] = (uint8_t)b;    // literals: window lanes 1..ll
+            lz_expand_period_from_window(out + op + ll, ml, off, b, 1u + ll - off, ul);
+            op += ll + ml;
+            ip += used;
+            continue;
+          }
+        }
+      }
+    }
     const uint32_t tag = in[ip++];
     uint32_t len, off;
     const uint32_t kind = tag & 3u;
@@ -174,7 +210,7 @@ struct SnappyDecode : SnappyPolicy {
 
 __device__ __forceinline__ bool snappy_decode_chunk_v2(const uint8_t* in, uint32_t in_n, uint8_t* out,
                                                        uint64_t out_cap, uint32_t* produced,
-                                                       uint8_t* ring, int lane, bool allow_direct = true) {
+                                                       uint8_t* ring, uint32_t& tma_parity, int lane, bool allow_direct = true) {
   uint32_t ip = 0;
   uint64_t ulen;
   if (!snappy_read_preamble(in, in_n, ip, ulen)) return false;
@@ -187,7 +223,10 @@ __device__ __forceinline__ bool snappy_decode_chunk_v2(const uint8_t* in, uint32
   s.ip = ip; s.op = 0; s.flushed = 0; s.ring_lo = 0;
   s.align = (uint32_t)((uintptr_t)out & 15u);
   s.ring = smem_addr(ring);
-  if (!lz_decode_stream<SnappyDecode>(s, lane)) return false;
+  s.cur = 0; s.pf_ip = kNoPrefetch; s.parity = tma_parity;
+  const bool ok = lz_decode_stream<SnappyDecode>(s, lane);
+  tma_parity = s.parity;                 // the barrier outlives the chunk: carry its phase to the next one
+  if (!ok) return false;
   if (s.op != (uint32_t)ulen) return false;
   *produced = s.op;
   return true;

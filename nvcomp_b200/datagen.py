@@ -22,10 +22,13 @@ def ref_gen_data(max_byte: int, size: int, rs: np.random.RandomState) -> np.ndar
     past = rng_range * scaling
     out = np.empty(size, dtype=np.uint8)
     filled = 0
+    bitgen = rs._bit_generator            # raw 32-bit mt19937 outputs, the sequence std::mt19937 produces
+    block = 1 << 22                       # cache-sized blocks: the 64-bit temporaries stay out of DRAM
     while filled < size:
-        raw = rs.randint(0, 1 << 32, size=size - filled, dtype=np.uint64)
-        # rejected draws are consumed and skipped, exactly like the C++ do/while loop
-        ok = raw[raw < past] // scaling
+        raw = bitgen.random_raw(min(block, size - filled))
+        if past != (1 << 32):
+            raw = raw[raw < past]         # rejected draws are consumed and skipped, exactly like the C++ do/while loop
+        ok = raw // scaling
         out[filled:filled + len(ok)] = ok.astype(np.uint8)
         filled += len(ok)
     return out

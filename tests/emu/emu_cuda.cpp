@@ -40,6 +40,8 @@ static void to_main() {
   emu_switch(&w->lanes[me].sp, w->main_sp);
 }
 
+void yield() { to_main(); }
+
 [[noreturn]] void fail(const char* fmt, ...) {
   Warp* w = g_warp;
   va_list ap;

@@ -58,6 +58,7 @@ extern thread_local Warp* g_warp;
 [[noreturn]] void fail(const char* fmt, ...);
 void run_warp(Warp& w, size_t smem_bytes, std::function<void(int)> body);
 void rendezvous(int opcode, const void* site);
+void yield();   // let the other lanes run (a lane spinning on shared state)
 int lane();
 
 inline void add_region(Warp& w, const void* p, size_t n, bool writable) {

@@ -43,14 +43,16 @@ int run(int codec, int mode, const uint8_t* src, size_t n, uint8_t* dst, size_t 
   bool ok = false;
   emu::run_warp(w, b200::kLzWarpSmem, [&](int lane) {
     uint8_t* ring = emu::g_warp->smem;
+    b200::lz_warp_init(b200::smem_addr(ring), lane);
+    uint32_t tma_parity = 0;
     uint32_t prod = 0;
     bool r;
     if (codec == 0) {
       r = mode == 1 ? b200::lz4_decode_chunk_direct(gin.p, (uint32_t)n, gout.p, cap, &prod, lane)
-                    : b200::lz4_decode_chunk_v2(gin.p, (uint32_t)n, gout.p, cap, &prod, ring, lane, mode != 2);
+                    : b200::lz4_decode_chunk_v2(gin.p, (uint32_t)n, gout.p, cap, &prod, ring, tma_parity, lane, mode != 2);
     } else {
       r = mode == 1 ? b200::snappy_decode_chunk(gin.p, (uint32_t)n, gout.p, cap, &prod, lane)
-                    : b200::snappy_decode_chunk_v2(gin.p, (uint32_t)n, gout.p, cap, &prod, ring, lane, mode != 2);
+                    : b200::snappy_decode_chunk_v2(gin.p, (uint32_t)n, gout.p, cap, &prod, ring, tma_parity, lane, mode != 2);
     }
     if (lane == 0) { ok = r; produced = prod; }
   });

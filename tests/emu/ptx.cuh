@@ -65,4 +65,24 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
   return p[O];
 }
 
+// mbarrier + TMA bulk copy: the copy completes at once; the barrier is a phase counter in the 8 bytes it occupies
+// and a waiting lane yields to the other fibers until the phase it waits for has completed.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t) { uint32_t z = 0; memcpy(emu::smem_ptr(mbar, 8), &z, 4); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t, uint32_t) {}
+__device__ __forceinline__ void fence_proxy_async_smem() {}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t mbar) {
+  if ((smem_dst & 15u) || ((uintptr_t)gmem_src & 15u) || (bytes & 15u)) emu::fail("misaligned bulk copy");
+  emu::check_global(gmem_src, bytes, false);
+  memcpy(emu::smem_ptr(smem_dst, bytes), gmem_src, bytes);
+  uint32_t c; memcpy(&c, emu::smem_ptr(mbar, 8), 4); ++c; memcpy(emu::smem_ptr(mbar, 8), &c, 4);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (int spins = 0;; ++spins) {
+    uint32_t c; memcpy(&c, emu::smem_ptr(mbar, 8), 4);
+    if ((c & 1u) != parity) return;
+    if (spins > 1000000) emu::fail("mbar_wait never completes (parity %u)", parity);
+    emu::yield();
+  }
+}
+
 }  // namespace b200

@@ -58,7 +58,7 @@ def _streams(oracle, liblz4, data):
 def test_emulated_decoder_matches_cpu_codecs(emu, oracle, liblz4, name):
     data = INPUTS[name]
     for codec, producer, comp in _streams(oracle, liblz4, data):
-        for mode in ("adaptive", "block"):
+        for mode in ("adaptive", "block", "direct"):
             got = emu.decode(codec, comp, len(data), mode)
             assert got == data, (codec, producer, mode, name)
 
@@ -98,11 +98,12 @@ def test_emulated_decoder_rejects_malformed(emu, oracle):
                     bad[i] ^= 1 << int(rng.integers(0, 8))
                 bad = bytes(bad)
                 want = oracle.decompress(codec, bad, n)
-                got = emu.decode(codec, bad, n, "block")
-                if want is None:
-                    assert got is None
-                else:
-                    assert got == want
+                for mode in ("block", "direct"):
+                    got = emu.decode(codec, bad, n, mode)
+                    if want is None:
+                        assert got is None, mode
+                    else:
+                        assert got == want, mode
         garbage = rng.integers(0, 256, 5000, dtype=np.uint8).tobytes()
         want = oracle.decompress(codec, garbage, 65536)
         got = emu.decode(codec, garbage, 65536, "block")

@@ -3,7 +3,7 @@
 #   bash tools/collect_evidence.sh [tag]        -> gpurun_out/evidence/<tag>_*
 # Then, back in the build container: python tools/publish_evidence.py [tag] copies / summarises into profiles/.
 set -u
-TAG=${1:-r1}
+TAG=${1:-r2}
 O=gpurun_out/evidence
 mkdir -p $O
 declare -A DS=( [snappy]=tabular_f32 [lz4]=lz4_mixed [cascaded]=sorted_i64 [bitcomp]=sorted_i64 [ans]=lowentropy_bytes )
@@ -30,16 +30,25 @@ wc -l $O/${TAG}_lz_per_dataset.jsonl
 
 echo "== ncu: launch list of the default bench"
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-  --log-file $O/${TAG}_bench_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > $O/${TAG}_launches.log 2>&1
+  --log-file $O/${TAG}_bench_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $O/${TAG}_launches.log 2>&1
 wc -l $O/${TAG}_bench_launches.csv
 
 echo "== ncu: one full capture per decode kernel"
+declare -A KN=( [snappy]=snappy_decompress_v2 [lz4]=lz4_decompress_v2 [cascaded]=cascaded_decompress [bitcomp]=bitcomp_decompress [ans]=ans_decompress )
 for c in $CODECS; do
-  timeout 500 ncu --set full --clock-control none --import-source on -k regex:${c}_decompress -c 1 -f \
+  timeout 500 ncu --set full --clock-control none --import-source on -k regex:${KN[$c]} -c 1 -f \
     -o $O/${TAG}_${c}_${DS[$c]} python tools/quick_bench.py --codecs $c --datasets ${DS[$c]} --iters 2 --no-verify \
     > $O/${TAG}_ncu_$c.log 2>&1
   ls -la $O/${TAG}_${c}_${DS[$c]}.ncu-rep 2>&1 | cut -c1-120
 done
+# the dense block decoder alone on the survey's cfg2-ii column, and the light (direct) kernel on run-length data
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:snappy_decompress_v2 -c 1 -f \
+  -o $O/${TAG}_snappy_price_walk python tools/quick_bench.py --codecs snappy --datasets tabular_f32:0 --iters 2 --no-verify \
+  > $O/${TAG}_ncu_snappy_pw.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:lz4_decompress_light -c 1 -f \
+  -o $O/${TAG}_lz4_runlength_i32 python tools/quick_bench.py --codecs lz4 --datasets runlength_i32 --iters 2 --no-verify \
+  > $O/${TAG}_ncu_lz4_rl.log 2>&1
+ls -la $O/${TAG}_snappy_price_walk.ncu-rep $O/${TAG}_lz4_runlength_i32.ncu-rep 2>&1 | cut -c1-120
 
 echo "== compute-sanitizer memcheck"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_fuzz_gpu.py -x -q -m gpu \

@@ -12,7 +12,7 @@ import shutil
 import subprocess
 import sys
 
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "gpurun_out", "evidence")
 DST = os.path.join(ROOT, "profiles")
@@ -60,7 +60,7 @@ def main():
             cnt[r[k_i]] += 1
     total = sum(tot.values())
     with open(os.path.join(DST, f"{TAG}_bench_launch_list.md"), "w") as f:
-        f.write(f"# round {TAG[1:]} — launch list of `python bench.py --steps 3 --warmup 3 --no-cpu` (snappy, tabular_f32)\n\n")
+        f.write(f"# round {TAG[1:]} — launch list of `python bench.py --steps 3 --warmup 3 --no-cpu --no-extras` (snappy, tabular_f32)\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised: compare "
                 f"shares, not absolutes). Raw CSV: `{TAG}_bench_launches.csv`.\n\n| kernel | launches | total time | share |\n|---|---|---|---|\n")
         for k, v in tot.most_common():
@@ -77,6 +77,15 @@ def main():
         val, unit = ncu_raw(rep)
         traffic[f"{c}:{ds}"] = int(to_bytes(val["dram__bytes_read.sum"], unit["dram__bytes_read.sum"]) +
                                    to_bytes(val["dram__bytes_write.sum"], unit["dram__bytes_write.sum"]))
+    for name, title in (("snappy_price_walk", "snappy dense block decoder, 10000 x 64 KB chunks (tabular_f32:0, price-walk column)"),
+                        ("lz4_runlength_i32", "lz4 light (direct) kernel, 10000 x 64 KB chunks (runlength_i32)")):
+        rep = os.path.join(SRC, f"{TAG}_{name}.ncu-rep")
+        if os.path.exists(rep):
+            md = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, f"round {TAG[1:]} — {title}"],
+                                capture_output=True, text=True).stdout
+            open(os.path.join(DST, f"{TAG}_{name}_ncu_summary.md"), "w").write(md)
+    traffic["_source"] = (f"profiles/{TAG}_<codec>_<dataset>_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                          "`ncu --set full` capture of the named decode kernel on this workload (not measured in the bench run)")
     json.dump(traffic, open(os.path.join(DST, "traffic.json"), "w"), indent=1)
     print(json.dumps(traffic))
 
