@@ -365,13 +365,15 @@ class DistributedJob:
             self.recv_buf = torch.zeros(w.comp_span + 64, dtype=torch.uint8, device=dev)
             self.recv_ptrs = torch.from_numpy(w.c_offs + self.recv_buf.data_ptr()).to(dev)
         self.comm = torch.cuda.Stream()
+        self.dstreams = [torch.cuda.Stream() for _ in range(self.NSLICES)]
         self.temps = [torch.empty(max(w.tb, 1), dtype=torch.uint8, device=dev) for _ in range(self.NSLICES)]
         self.dist = dist
         self.torch = torch
 
     def step(self, decode=True):
         """One job: every slice of every remote rank's share leaves rank 0 on the comm stream; a rank decodes slice i
-        as soon as it has arrived (rank 0 decodes its own share from the slab it already holds)."""
+        on its own stream as soon as it has arrived (one 2,500-chunk launch alone would be bounded by the latency of a
+        single chunk, so the slices' launches overlap); rank 0 decodes its own share from the slab it already holds."""
         torch, dist, w = self.torch, self.dist, self.w
         cur = torch.cuda.current_stream()
         self.comm.wait_stream(cur)                       # the previous job's decode has consumed the buffers
@@ -387,14 +389,24 @@ class DistributedJob:
                 else:
                     lo, hi = self.spans[i]
                     works.append(dist.batch_isend_irecv([dist.P2POp(dist.irecv, self.recv_buf[lo:hi], 0)]))
-        for i in range(self.NSLICES):
-            a, b = self.bounds[i], self.bounds[i + 1]
-            if self.rank != 0:
-                for wk in works[i]:
-                    wk.wait()                            # the current (decode) stream waits for this slice only
-            if decode:
-                w.launch(cur.cuda_stream, ptrs=None if self.rank == 0 else self.recv_ptrs, a=a, b=b, temp=self.temps[i])
-        if self.rank == 0:
+        if decode and self.rank == 0:
+            w.launch(cur.cuda_stream)                    # own share: nothing to wait for, one launch
+        elif decode:
+            for i in range(self.NSLICES):
+                a, b = self.bounds[i], self.bounds[i + 1]
+                st = self.dstreams[i]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    for wk in works[i]:
+                        wk.wait()                        # this slice's stream waits for this slice only
+                    w.launch(st.cuda_stream, ptrs=self.recv_ptrs, a=a, b=b, temp=self.temps[i])
+            for st in self.dstreams:
+                cur.wait_stream(st)
+        else:
+            for ws in works:
+                for wk in ws:
+                    wk.wait()
+        if self.rank == 0 and decode:
             for ws in works:
                 for wk in ws:
                     wk.wait()

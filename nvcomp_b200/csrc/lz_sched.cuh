@@ -65,18 +65,27 @@ struct LzWork {
   const size_t* comp_bytes;
   const size_t* out_caps;
   size_t batch, static_next, static_stride;
-  bool want_light;
+  bool want_light, first;
   __device__ __forceinline__ LzWork(const LzLists& l, bool light, const size_t* cb, const size_t* oc, size_t n,
                                     size_t warp_global, size_t warps_total)
       : list(l.ctr ? (light ? l.light : l.dense) : nullptr), count(l.ctr ? l.ctr[light ? 2 : 3] : 0),
         ticket(l.ctr ? l.ctr + (light ? 0 : 1) : nullptr), comp_bytes(cb), out_caps(oc), batch(n),
-        static_next(warp_global), static_stride(warps_total), want_light(light) {}
+        static_next(warp_global), static_stride(warps_total), want_light(light), first(true) {}
   // next chunk of this warp, or batch when there is none
   __device__ __forceinline__ size_t next(int lane) {
     if (list) {
-      unsigned long long t = 0;
-      if (lane == 0) t = atomicAdd(ticket, 1ull);
-      t = __shfl_sync(kFull, t, 0);
+      // The first chunk of every warp is static (list entry = global warp index), the rest come from the ticket.  With
+      // fewer chunks than resident warps this packs the work into whole CTAs -- the CTAs behind them retire at once --
+      // instead of leaving every resident CTA half idle while it still holds its shared memory and registers.
+      unsigned long long t;
+      if (first) {
+        first = false;
+        t = static_next;
+      } else {
+        t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1ull);
+        t = __shfl_sync(kFull, t, 0) + static_stride;
+      }
       return t < count ? (size_t)list[t] : batch;
     }
     while (static_next < batch) {
