@@ -384,17 +384,30 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
     }
     __syncwarp();
     // ---- matches
-    // Sources below the step are final.  A match that reads bytes produced in this same step ("in-window") is simply
-    // re-copied until a whole round changes nothing: every lane copies what currently stands at its source, so after
-    // round r every dependency chain of depth <= r is right, and a round in which no lane loaded anything new is a
-    // fixpoint -- which, walking the matches in stream order, can only be the correct output.  No dependency
-    // analysis, no per-lane gating; the price is one confirming round (3.6 + 1 rounds on the price-walk column).
     const unsigned hasm = __ballot_sync(kFull, has);
     if (hasm) {
       const uint32_t cur_op = s.op;
       const uint32_t ring_from = max(s.ring_lo, cur_op > kRingReach ? cur_op - kRingReach : 0u) + s.align;
       const uint32_t src = o_mat - off;
-      const bool inwin = has && src + min(M, off) > step_lo;    // reads bytes produced in this step
+      const uint32_t src_end = src + min(M, off);              // exclusive end of the bytes this match reads
+      // which tokens of this step produce my source bytes?  Token ranges are consecutive, so the
+      // producers are the lanes from the one holding byte max(src, step_lo) to the one holding src_end-1
+      // (own literals precede the own match in program order: the self bit is dropped).
+      unsigned dep = 0;
+      const bool inwin = has && src_end > step_lo;
+      if (__any_sync(kFull, inwin)) {
+        const uint32_t key = valid ? dst : 0xffffffffu;
+        const uint32_t qa = max(src, step_lo), qb = src_end - 1u;
+        uint32_t ja = 0, jb = 0;
+#pragma unroll
+        for (uint32_t st = 16; st; st >>= 1) {
+          const uint32_t va = __shfl_sync(kFull, key, (int)(ja + st));
+          const uint32_t vb = __shfl_sync(kFull, key, (int)(jb + st));
+          if (va <= qa) ja += st;
+          if (vb <= qb) jb += st;
+        }
+        if (inwin) dep = ((2u << jb) - 1u) & ~((1u << ja) - 1u) & ~(1u << ul);
+      }
       const uint32_t sidx = src & kRingMask;
       const bool in_ring = src >= ring_from && sidx + M + 8u <= kRingBytes;
       const bool far = src + M <= ring_from;                   // flushed long ago: read from global memory
@@ -403,7 +416,7 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
       const bool simple = !wrap && off >= 4u && M >= 4u && (in_ring || far);
       const bool c_r = has && simple && !far, c_g = has && simple && far, c_b = has && !simple;
       const uint32_t dp = rbase + (o_mat & kRingMask);
-      // sources flushed long ago: one pass, outside the rounds
+      // sources flushed long ago are final: those matches run first, outside the rounds
       if (__any_sync(kFull, c_g)) {
         if (c_g) {
           const uint8_t* const gp = outa + src;
@@ -421,75 +434,62 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
             if (M > g + 3u) sts_u8<3>(d4, x3);
           }
         }
-        __syncwarp();                                           // their bytes may feed round 0
+        __syncwarp();                                           // their bytes may feed round 1
       }
-      // round 0: every ring match; rounds 1..: the in-window ones, until nothing changes
-      unsigned a_b = __ballot_sync(kFull, c_b);
-      unsigned a_4 = __ballot_sync(kFull, c_r && M > 4u), a_8 = __ballot_sync(kFull, c_r && M > 8u);
-      const unsigned inwm = __ballot_sync(kFull, inwin && !c_g);
+      const unsigned m_b = __ballot_sync(kFull, c_b);
+      const unsigned m_4 = __ballot_sync(kFull, c_r && M > 4u);
+      const unsigned m_8 = __ballot_sync(kFull, c_r && M > 8u);
+      unsigned done = ~__ballot_sync(kFull, c_r || c_b);
+      bool pend = c_r || c_b;
       const uint32_t sa = rbase + (sidx & ~3u), sh = (sidx & 3u) * 8u;   // aligned words around the source
-      const uint32_t keep1 = M >= 8u ? 0xffffffffu : ~(0xffffffffu << (8u * (M & 3u)));   // bytes 4..M-1 of a 5..7-byte match
-      bool act_r = c_r, act_b = c_b;
-      uint32_t p0 = 0, p1 = 0;
-      for (uint32_t round = 0;; ++round) {
-        uint32_t ch = 0;
-        if (act_r) {
+      while (done != kFull) {
+        const bool ready = pend && (dep & ~done) == 0u;
+        const unsigned rm = __ballot_sync(kFull, ready);
+        const bool go = ready && c_r;
+        if (go) {
           const uint32_t x = __funnelshift_r(lds_u32(sa), lds_u32(sa + 4u), sh);
-          ch = x ^ p0;
-          p0 = x;
           sts_u8<0>(dp, x);
           sts_u8<1>(dp, x >> 8);
           sts_u8<2>(dp, x >> 16);
           sts_u8<3>(dp, x >> 24);
         }
-        if (a_4) {
-          if (act_r && M > 4u) {                               // (reloaded: with off < 8 these are bytes stored just above)
-            const uint32_t x = __funnelshift_r(lds_u32(sa + 4u), lds_u32(sa + 8u), sh) & keep1;
-            ch |= x ^ p1;
-            p1 = x;
+        if (rm & m_4) {
+          if (go && M > 4u) {                                  // (reloaded: with off < 8 these are bytes stored just above)
+            const uint32_t x = __funnelshift_r(lds_u32(sa + 4u), lds_u32(sa + 8u), sh);
             sts_u8<4>(dp, x);
             if (M > 5u) sts_u8<5>(dp, x >> 8);
             if (M > 6u) sts_u8<6>(dp, x >> 16);
             if (M > 7u) sts_u8<7>(dp, x >> 24);
           }
         }
-        if (a_b | a_8) {
-          if (a_b) {
-            // short periods / copies, ring wrap-around, sources straddling the flushed boundary: byte by byte,
-            // in order (a byte may read what this loop wrote off bytes earlier)
-            if (act_b) {
-              for (uint32_t j = 0; j < M; ++j) {
-                const uint32_t q = src + j;
-                const uint32_t b = (q >= ring_from) ? lds_u8(rbase + (q & kRingMask)) : (uint32_t)outa[q];
-                const uint32_t da = rbase + ((o_mat + j) & kRingMask);
-                ch |= b ^ lds_u8(da);
-                sts_u8(da, b);
-              }
-            }
-          }
-          __syncwarp();
-          // bytes 8.. of the long matches: whole warp, one match per pass (M <= 32).  Byte j of an overlapping
-          // match (off < M) repeats byte j mod off.
-          for (unsigned longm = a_8; longm; longm &= longm - 1u) {
-            const int t = __ffs((int)longm) - 1;
-            const uint32_t tM = __shfl_sync(kFull, M, t), toff = __shfl_sync(kFull, off, t);
-            const uint32_t tsp = __shfl_sync(kFull, sidx, t), tdp = __shfl_sync(kFull, dp, t);
-            const uint32_t j = 8u + ul;
-            if (j < tM) {
-              const uint32_t b = lds_u8(rbase + tsp + (toff < tM ? j % toff : j));
-              ch |= b ^ lds_u8(tdp + j);
-              sts_u8(tdp + j, b);
+        if (rm & m_b) {
+          // short periods / copies, ring wrap-around, sources straddling the flushed boundary: byte by byte,
+          // in order (a byte may read what this loop wrote off bytes earlier)
+          if (ready && c_b) {
+            for (uint32_t j = 0; j < M; ++j) {
+              const uint32_t q = src + j;
+              const uint32_t b = (q >= ring_from) ? lds_u8(rbase + (q & kRingMask)) : (uint32_t)outa[q];
+              sts_u8(rbase + ((o_mat + j) & kRingMask), b);
             }
           }
         }
         __syncwarp();
-        if (round == 0u) {
-          if (inwm == 0u) break;                                // nothing reads this step's own output
-          act_r = act_r && inwin; act_b = act_b && inwin;      // from now on only the in-window matches
-          a_4 &= inwm; a_8 &= inwm; a_b &= inwm;
-          continue;
+        unsigned longm = rm & m_8;
+        if (longm) {
+          // bytes 8.. of the long matches that just ran: whole warp, one match per round (M <= 32).  Byte j of an
+          // overlapping match (off < M) repeats byte j mod off.
+          do {
+            const int t = __ffs((int)longm) - 1;
+            longm &= longm - 1u;
+            const uint32_t tM = __shfl_sync(kFull, M, t), toff = __shfl_sync(kFull, off, t);
+            const uint32_t tsp = __shfl_sync(kFull, sidx, t), tdp = __shfl_sync(kFull, dp, t);
+            const uint32_t j = 8u + ul;
+            if (j < tM) sts_u8(tdp + j, lds_u8(rbase + tsp + (toff < tM ? j % toff : j)));
+          } while (longm);
+          __syncwarp();
         }
-        if (!__any_sync(kFull, ch != 0u)) break;
+        done |= rm;
+        pend = pend && !ready;
       }
     }
     s.op += step_out;
