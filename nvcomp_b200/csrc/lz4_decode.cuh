@@ -192,7 +192,7 @@ __device__ __forceinline__ bool lz4_decode_chunk_v2(const uint8_t* in, uint32_t 
   s.ip = 0; s.op = 0; s.flushed = 0; s.ring_lo = 0;
   s.align = (uint32_t)((uintptr_t)out & 15u);
   s.ring = smem_addr(ring);
-  s.cur = 0; s.pf_ip = kNoPrefetch; s.parity = tma_parity;
+  s.cur = 0; s.pf_ip = kNoPrefetch; s.parity = tma_parity; s.next = kNextUnknown;
   const bool ok = lz_decode_stream<Lz4Decode>(s, lane);
   tma_parity = s.parity;                 // the barrier outlives the chunk: carry its phase to the next one
   if (!ok) return false;

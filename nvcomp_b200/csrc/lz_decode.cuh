@@ -48,8 +48,10 @@ struct LzState {
   uint32_t cur;        // buffer that holds the block being parsed
   uint32_t pf_ip;      // input position whose block is being prefetched into the other buffer (kNoPrefetch: none)
   uint32_t parity;     // phase parity the next mbarrier wait uses
+  uint32_t next;       // what the driver knows about the token at ip (kNext*)
 };
 constexpr uint32_t kNoPrefetch = 0xffffffffu;
+constexpr uint32_t kNextUnknown = 0, kNextSerial = 1, kNextBlock = 2;
 
 __device__ __forceinline__ uint32_t ring_idx(const LzState& s, uint32_t off) {
   return (off + s.align) & kRingMask;
@@ -94,6 +96,7 @@ __device__ __forceinline__ void lz_flush_blocks(LzState& s, int lane) {
 // fields() extracts literal length / match length / offset for execution.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kTokStop = 64;
+constexpr uint32_t kTokExt = 0x80;      // sizes4 marker: the size depends on an extension byte (P::ext_size)
 constexpr uint32_t kMaxTokOut = 32;     // output bytes of one fast token (32 tokens x 32 bytes = one step)
 
 // 4 bytes at an arbitrary position of a shared-memory buffer (two aligned words + funnel shift)
@@ -107,13 +110,23 @@ __device__ __forceinline__ uint32_t lane_private(uint32_t p) { return (p >> 2) *
 __device__ __forceinline__ uint32_t byte_mask(uint32_t x) { return (x << 8) - x; }
 
 struct Lz4Policy {
-  // sequence: token, L literals, 2-byte offset; fast when neither nibble is 15
+  // sequence: token, L literals, 2-byte offset; fast when the literal nibble is < 15.  A match nibble of 15 is
+  // followed by length-extension bytes: sizes4 marks it kTokExt | (size with one extension byte) and the chain
+  // step (lz_block) looks at that byte -- one byte below 14 - L keeps the token fast (M = 19 + ext, L + M <= 32).
+  static constexpr bool kHasExt = true;
   __device__ static __forceinline__ uint32_t sizes4(uint32_t w) {
     const uint32_t L = (w >> 4) & 0x0f0f0f0fu, Mn = w & 0x0f0f0f0fu;
     // nibble == 15  <=>  nibble + 1 carries into bit 4
-    const uint32_t stop = (((L + 0x01010101u) | (Mn + 0x01010101u)) >> 4) & 0x01010101u;
-    const uint32_t sm = byte_mask(stop);
-    return ((L + 0x03030303u) & ~sm) | (sm & 0x40404040u);
+    const uint32_t stop = byte_mask(((L + 0x01010101u) >> 4) & 0x01010101u);
+    const uint32_t ext = ((Mn + 0x01010101u) >> 4) & 0x01010101u;
+    const uint32_t sz = L + 0x03030303u + ext;                 // + 1 extension byte
+    return ((sz | (ext << 7)) & ~stop) | (stop & 0x40404040u);
+  }
+  // size of a token sizes4 marked kTokExt: blk/pos locate the token, marked = kTokExt | (4 + L)
+  __device__ static __forceinline__ uint32_t ext_size(uint32_t blk, uint32_t pos, uint32_t marked) {
+    const uint32_t sz = marked & 0x7fu;                        // 4 + L
+    const uint32_t ext = lds_u8(blk + pos + sz - 1u);
+    return ext + sz < 18u ? sz : kTokStop;                     // ext < 14 - L
   }
   __device__ static __forceinline__ void fields(uint32_t blk, uint32_t pos, uint32_t& L, uint32_t& M,
                                                 uint32_t& off, uint32_t& lit_at) {
@@ -121,14 +134,22 @@ struct Lz4Policy {
     L = (x >> 4) & 15u;
     M = (x & 15u) + 4u;
     lit_at = pos + 1u;
-    off = (x >> 8) & 0xffffu;
-    if (L) off = lds_u32_any(blk, pos + 1u + L) & 0xffffu;
+    uint32_t y = x >> 8;                                       // offset (2 bytes), first extension byte
+    if (L) y = lds_u32_any(blk, pos + 1u + L);
+    off = y & 0xffffu;
+    if (M == 19u) M += (y >> 16) & 0xffu;
   }
-  // does the token starting with byte b0 need the serial path?
-  __device__ static __forceinline__ bool is_stop(uint32_t b0) { return (b0 >> 4) == 15u || (b0 & 15u) == 15u; }
+  // does the token at p need the serial path?  (p has at least kSegBytes readable bytes)
+  __device__ static __forceinline__ bool is_stop(const uint8_t* __restrict__ p) {
+    const uint32_t b0 = p[0], L = b0 >> 4;
+    if (L == 15u) return true;
+    return (b0 & 15u) == 15u && (uint32_t)p[3u + L] + L > 13u;
+  }
 };
 
 struct SnappyPolicy {
+  static constexpr bool kHasExt = false;
+  __device__ static __forceinline__ uint32_t ext_size(uint32_t, uint32_t, uint32_t) { return kTokStop; }
   // literal (kind 0): 1 + (h+1) bytes, fast up to 31 literal bytes; copy-1: 2 bytes; copy-2: 3 bytes, fast up to
   // kMaxTokOut output bytes; copy-4: serial
   __device__ static __forceinline__ uint32_t sizes4(uint32_t w) {
@@ -153,7 +174,8 @@ struct SnappyPolicy {
     M = kind == 0u ? 0u : len;
     off = kind == 1u ? ((x >> 5) & 7u) << 8 | ((x >> 8) & 255u) : (x >> 8) & 0xffffu;
   }
-  __device__ static __forceinline__ bool is_stop(uint32_t b0) {
+  __device__ static __forceinline__ bool is_stop(const uint8_t* __restrict__ p) {
+    const uint32_t b0 = p[0];
     const uint32_t kind = b0 & 3u, h = b0 >> 2;
     return kind == 3u || (kind == 0u && h >= 31u) || (kind == 2u && h >= 32u);
   }
@@ -250,9 +272,11 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
     sts_u32(my_sz + 128u * i, w[i]);
   }
   // ---- 2. chain: exit table of this lane's segment (code >= 32: the chain ends in a stop token) ----
+  // (a size that depends on an extension byte -- sizes4 marked it kTokExt -- counts with its one-byte form here; the
+  // walk below looks at the byte for the tokens that are really on the chain and ends the block where it is not)
 #pragma unroll
   for (int p = 31; p >= 0; --p) {
-    const uint32_t q = (uint32_t)p + ((w[p >> 2] >> (8 * (p & 3))) & 255u);
+    const uint32_t q = (uint32_t)p + ((w[p >> 2] >> (8 * (p & 3))) & (P::kHasExt ? 0x7fu : 0xffu));
     const uint32_t code = (q >= kSegBytes) ? q - kSegBytes : lds_u8(my_ex + lane_private(q));
     sts_u8(my_ex + (uint32_t)(128 * (p >> 2) + (p & 3)), code);
   }
@@ -273,17 +297,28 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
   }
   const uint32_t my_exit = lds_u8(my_ex + lane_private(e));
   const unsigned stopm = __ballot_sync(kFull, ul < nl && my_exit >= kSegBytes);
-  const uint32_t stop_lane = stopm ? (uint32_t)__ffs((int)stopm) - 1u : 32u;
+  uint32_t stop_lane = stopm ? (uint32_t)__ffs((int)stopm) - 1u : 32u;
   // ---- 3. walk: tokens of this lane's segment ------------------------------------------------------
   const bool active = ul < nl && ul <= stop_lane;
   uint32_t p = e, cnt = 0;
+  bool ext_stop = false;
   if (active) {
     while (p < kSegBytes) {
-      const uint32_t sz = lds_u8(my_sz + lane_private(p));
+      uint32_t sz = lds_u8(my_sz + lane_private(p));
       if (sz == kTokStop) break;
+      if (P::kHasExt && (sz & kTokExt)) {
+        sz = P::ext_size(blk, kSegBytes * ul + p, sz);
+        if (sz == kTokStop) { ext_stop = true; break; }
+      }
       ++cnt;
       p += sz;
     }
+  }
+  if (P::kHasExt) {
+    // a token whose extension byte makes it long is a stop token after all: the block ends there
+    const unsigned em = __ballot_sync(kFull, ext_stop);
+    if (em) stop_lane = min(stop_lane, (uint32_t)__ffs((int)em) - 1u);
+    if (ul > stop_lane) cnt = 0;
   }
   // block end: the stop token, or where the chain leaves the last segment
   const uint32_t end_pos = __shfl_sync(kFull, kSegBytes * ul + p, (int)(stop_lane < 32u ? stop_lane : nl - 1u));
@@ -300,7 +335,7 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
     uint32_t ra = rec + 2u * (incl - cnt), q = e;
     for (uint32_t j = 0; j < cnt; ++j) {
       sts_u16(ra, kSegBytes * ul + q);
-      q += lds_u8(my_sz + lane_private(q));
+      q += lds_u8(my_sz + lane_private(q)) & (P::kHasExt ? 0x7fu : 0xffu);
       ra += 2u;
     }
   }
@@ -497,6 +532,8 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
     lz_flush_blocks(s, lane);
   }
   s.ip += end_pos - mis;
+  // what the caller meets at s.ip now: a stop token (the chain ended in one) or the next block (prefetched)
+  s.next = stop_lane < 32u ? kNextSerial : kNextBlock;
   return (int)N;
 }
 
@@ -623,9 +660,13 @@ template <class P>
 __device__ __forceinline__ bool lz_decode_loop(LzState& s, int lane) {
   while (true) {
     if (P::at_end(s)) break;
-    // a token that needs the serial path is recognised from its first byte: do not pay for a
-    // block parse that would retire nothing
-    if (s.in_n - s.ip >= kSegBytes + kBlkPad && !P::is_stop(s.in[s.ip])) {
+    // A token that needs the serial path is recognised from its first bytes: do not pay for a block parse that
+    // would retire nothing.  The peek is a global load the whole warp waits for, so it is only made when the
+    // previous step does not already tell: a block that ended in a stop token is followed by that token, a block that
+    // ran to its end is followed by the next (prefetched) block.
+    const uint32_t next = s.next;
+    s.next = kNextUnknown;
+    if (next != kNextSerial && s.in_n - s.ip >= kSegBytes + kBlkPad && (next == kNextBlock || !P::is_stop(s.in + s.ip))) {
       const int r = lz_block<P>(s, lane);
       if (r < 0) return false;
       if (r > 0) continue;
