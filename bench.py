@@ -302,7 +302,12 @@ class Workload:
     def check(self):
         import torch
         torch.cuda.synchronize()
-        assert bool((self.status == 0).all().item()) and bool((self.actual == CHUNK).all().item()), "decompress status/size"
+        if not (bool((self.status == 0).all().item()) and bool((self.actual == CHUNK).all().item())):
+            st, ac = self.status.cpu().numpy(), self.actual.cpu().numpy()
+            bad = np.nonzero((st != 0) | (ac != CHUNK))[0]
+            raise AssertionError(f"decompress status/size: {len(bad)} of {self.n} chunks, first {bad[:8].tolist()}, "
+                                 f"status {st[bad[:8]].tolist()}, actual {ac[bad[:8]].tolist()}, "
+                                 f"comp sizes {self.c_sizes[bad[:8]].tolist()}")
         assert torch.equal(self.out.slab[: self.total], self.inp.slab[: self.total]), "decompressed bytes differ from the input"
 
     def reset_outputs(self):
@@ -485,11 +490,13 @@ def foreign_streams(kind, base: Workload, args, peak):
 
         def lz4_default(raw):
             buf = C.create_string_buffer(cap)
-            return buf.raw[: lz4.LZ4_compress_default(raw, buf, len(raw), cap)]
+            n_ = lz4.LZ4_compress_default(raw, buf, len(raw), cap)   # before buf.raw: that makes a copy
+            return buf.raw[:n_]
 
         def lz4_hc(raw):
             buf = C.create_string_buffer(cap)
-            return buf.raw[: lz4.LZ4_compress_HC(raw, buf, len(raw), cap, 12)]
+            n_ = lz4.LZ4_compress_HC(raw, buf, len(raw), cap, 12)
+            return buf.raw[:n_]
         producers.append(("liblz4_default", n, lz4_default))
         producers.append(("liblz4_hc12", min(n, 4000), lz4_hc))     # HC-12 is slow to produce: bounded sample, stated
     for name, m, fn in producers:

@@ -225,7 +225,8 @@ __device__ __forceinline__ void lz_stage_wait(LzState& s) {
 }
 // lane 0 starts the bulk copy of `bytes` (multiple of 16) from the 16-byte aligned `src` into block buffer `buf`
 __device__ __forceinline__ void lz_stage_issue(const LzState& s, uint32_t buf, const uint8_t* src, uint32_t bytes, int lane) {
-  __syncwarp();                                     // every lane is done with the buffer (generic proxy) ...
+  fence_proxy_async_smem();                         // every lane's generic-proxy accesses to the buffer are ordered
+  __syncwarp();                                     // ... and done ...
   if (lane == 0) {
     fence_proxy_async_smem();                       // ... before the async proxy overwrites it
     mbar_expect_tx(s.ring + kSmemMbar, bytes);

@@ -41,6 +41,14 @@ for c in $CODECS; do
     > $O/${TAG}_ncu_$c.log 2>&1
   ls -la $O/${TAG}_${c}_${DS[$c]}.ncu-rep 2>&1 | cut -c1-120
 done
+# DRAM traffic of the light (direct) kernel of the two LZ codecs on the bench workloads: the bench's `traffic` is the
+# sum over both decode kernels of one DecompressAsync
+for c in snappy lz4; do
+  timeout 400 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:${c}_decompress_light -c 1 --csv \
+    --log-file $O/${TAG}_traffic_light_$c.csv python tools/quick_bench.py --codecs $c --datasets ${DS[$c]} --iters 2 --no-verify \
+    > $O/${TAG}_ncu_light_$c.log 2>&1
+  tail -2 $O/${TAG}_traffic_light_$c.csv | cut -c1-200
+done
 # the dense block decoder alone on the survey's cfg2-ii column, and the light (direct) kernel on run-length data
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:snappy_decompress_v2 -c 1 -f \
   -o $O/${TAG}_snappy_price_walk python tools/quick_bench.py --codecs snappy --datasets tabular_f32:0 --iters 2 --no-verify \

@@ -77,6 +77,14 @@ def main():
         val, unit = ncu_raw(rep)
         traffic[f"{c}:{ds}"] = int(to_bytes(val["dram__bytes_read.sum"], unit["dram__bytes_read.sum"]) +
                                    to_bytes(val["dram__bytes_write.sum"], unit["dram__bytes_write.sum"]))
+        light = os.path.join(SRC, f"{TAG}_traffic_light_{c}.csv")
+        if os.path.exists(light):   # LZ codecs: add the light kernel of the same DecompressAsync
+            lrows = list(csv.reader(open(light)))
+            hi = next(i for i, r in enumerate(lrows) if r and r[0] == "ID")
+            h = lrows[hi]
+            for r in lrows[hi + 1:]:
+                if len(r) > h.index("Metric Value") and r[h.index("Metric Name")].startswith("dram__bytes"):
+                    traffic[f"{c}:{ds}"] += int(to_bytes(r[h.index("Metric Value")].replace(",", ""), r[h.index("Metric Unit")]))
     for name, title in (("snappy_price_walk", "snappy dense block decoder, 10000 x 64 KB chunks (tabular_f32:0, price-walk column)"),
                         ("lz4_runlength_i32", "lz4 light (direct) kernel, 10000 x 64 KB chunks (runlength_i32)")):
         rep = os.path.join(SRC, f"{TAG}_{name}.ncu-rep")
@@ -85,7 +93,8 @@ def main():
                                 capture_output=True, text=True).stdout
             open(os.path.join(DST, f"{TAG}_{name}_ncu_summary.md"), "w").write(md)
     traffic["_source"] = (f"profiles/{TAG}_<codec>_<dataset>_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one "
-                          "`ncu --set full` capture of the named decode kernel on this workload (not measured in the bench run)")
+                          "`ncu --set full` capture of the named decode kernel on this workload (not measured in the bench run); for snappy / lz4 plus the "
+                          f"same two counters of the light kernel of that DecompressAsync ({TAG}_traffic_light_<codec>.csv)")
     json.dump(traffic, open(os.path.join(DST, "traffic.json"), "w"), indent=1)
     print(json.dumps(traffic))
 
