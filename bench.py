@@ -503,9 +503,16 @@ def foreign_streams(kind, base: Workload, args, peak):
         data = base.data[:m]
         with ThreadPoolExecutor(max_workers=min(64, os.cpu_count() or 1)) as ex:
             chunks = list(ex.map(lambda i: fn(data[i].tobytes()), range(m)))
-        w = Workload(kind, base.dataset, m, data=data, comp_chunks=chunks)
+        # a sample smaller than the batch is decoded reps times over (every stream into its own output chunk), so
+        # the launch fills the GPU like the other lines: a 4000-chunk launch is one partial wave of warps
+        reps = max(1, -(-n // m))
+        if reps > 1:
+            data, chunks = np.concatenate([data] * reps), chunks * reps
+        w = Workload(kind, base.dataset, m * reps, data=data, comp_chunks=chunks)
         ms, _ = time_decode(w, max(5, args.steps // 2), 3)
         out[name] = rate_line(w, ms, peak)
+        if reps > 1:
+            out[name]["distinct_chunks"] = m
         del w
     return out
 

@@ -103,8 +103,8 @@ __device__ __forceinline__ uint64_t unpack_at(const uint64_t* __restrict__ words
   if (bits == 0) return minv;
   const uint64_t bitpos = (uint64_t)k * bits;
   const uint32_t w = (uint32_t)(bitpos >> 6), s = (uint32_t)(bitpos & 63);
-  uint64_t v = words[w] >> s;
-  if (s + bits > 64) v |= words[w + 1] << (64 - s);
+  uint64_t v = __ldg(words + w) >> s;
+  if (s + bits > 64) v |= __ldg(words + w + 1) << (64 - s);
   if (bits < 64) v &= ((1ull << bits) - 1ull);
   return v + minv;
 }
@@ -115,14 +115,188 @@ __device__ __forceinline__ uint64_t unpack32_at(const uint32_t* __restrict__ w32
                                                 uint32_t bits, uint32_t mask, uint64_t minv) {
   const uint32_t bitpos = k * bits;                  // < 2^19: count <= 16384, bits <= 32
   const uint32_t w = bitpos >> 5, s = bitpos & 31u;
-  const uint32_t lo = w32[w];
-  const uint32_t hi = (s + bits > 32u) ? w32[w + 1] : 0u;
+  const uint32_t lo = __ldg(w32 + w);
+  const uint32_t hi = (s + bits > 32u) ? __ldg(w32 + w + 1) : 0u;
   return (uint64_t)(__funnelshift_r(lo, hi, s) & mask) + minv;
 }
 
 __host__ __device__ inline uint32_t stream_bytes(uint32_t count, uint32_t bits) {
   return 16u + 8u * (uint32_t)(((uint64_t)count * bits + 63) / 64);
 }
+
+// ---------------------------------------------------------------------------
+// Layer 0 of a configuration with run-length encoding, in one pass: the lane that owns four consecutive runs
+// produces their values (straight from the packed stream when this is the only layer, else from the shared-memory
+// buffer the layers above left; with a delta layer the exclusive prefix sum is taken on the fly), their start
+// positions (prefix sum of the run lengths) and fills the runs into the staging buffer, which then leaves with
+// coalesced 16-byte stores.  Two warp scans per 128 runs; no head-flag array, no max-scan, no gather.
+// Shared memory is addressed with 32-bit window addresses (st.shared with immediate offsets).
+// SRC: 0 packed stream of <= 32-bit values, 1 packed stream (any width), 2 shared-memory values.
+// The run-length stream has <= 32-bit values (the caller checks).
+// ---------------------------------------------------------------------------
+template <int TS, int J>
+__device__ __forceinline__ void sts_elem(uint32_t a, typename ScanType<TS>::S v) {
+  if (TS == 1) asm volatile("st.shared.u8 [%0+%2], %1;" :: "r"(a), "r"((uint32_t)v), "n"(J * TS) : "memory");
+  else if (TS == 2) asm volatile("st.shared.u16 [%0+%2], %1;" :: "r"(a), "h"((uint16_t)v), "n"(J * TS) : "memory");
+  else if (TS == 4) asm volatile("st.shared.u32 [%0+%2], %1;" :: "r"(a), "r"((uint32_t)v), "n"(J * TS) : "memory");
+  else asm volatile("st.shared.u64 [%0+%2], %1;" :: "r"(a), "l"((uint64_t)v), "n"(J * TS) : "memory");
+}
+
+// raw value k (without the stream minimum) of a stream of `bits` <= 32 bit values; k is inside the stream
+__device__ __forceinline__ uint32_t unpack32_raw(const uint32_t* __restrict__ w32, uint32_t k, uint32_t bits, uint32_t mask) {
+  const uint32_t bitpos = k * bits;                  // < 2^19: count <= 16384, bits <= 32
+  const uint32_t w = bitpos >> 5, s = bitpos & 31u;
+  const uint32_t lo = __ldg(w32 + w);               // (read-only path: LDG, not a generic load)
+  const uint32_t hi = (s + bits > 32u) ? __ldg(w32 + w + 1) : 0u;
+  return __funnelshift_r(lo, hi, s) & mask;
+}
+
+template <int TS, int SRC>
+__device__ __forceinline__ bool casc_final_rle(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ vwords,
+                                               const StreamHdr vh, const typename Elem<TS>::T* cur, uint32_t count,
+                                               bool has_delta, uint64_t first, uint32_t c_in,
+                                               const StreamHdr rh, const uint64_t* __restrict__ rwords,
+                                               typename Elem<TS>::T* stage, uint32_t cap,
+                                               uint8_t* out, uint32_t n_out, int lane) {
+  using T = typename Elem<TS>::T;
+  using S = typename ScanType<TS>::S;                  // 32-bit wrapping sums suffice for <= 4-byte elements
+  uint32_t nvals = count;
+  if (has_delta) {
+    if (c_in == 0u) { if (count != 0u) return false; has_delta = false; }   // the layer saw an empty list
+    else { if (c_in != count + 1u || c_in > cap) return false; nvals = count + 1u; }
+  }
+  if (rh.count != nvals) return false;
+  if (nvals == 0u) return n_out == 0u;
+  // an empty (0-bit) stream has no words: point the loads at the payload header instead, the mask drops what they read
+  const uint32_t* const vw32 = vh.bits ? (const uint32_t*)vwords : (const uint32_t*)payload;
+  const uint32_t vmask = vh.bits >= 32u ? 0xffffffffu : ((1u << vh.bits) - 1u);
+  const S vmin = (S)vh.minv;
+  const uint32_t vlast = count ? count - 1u : 0u;      // (count == 0: one value, no deltas; nothing is read)
+  auto val = [&](uint32_t k) -> S {                    // k is clamped by the caller: every load stays inside the stream
+    if (SRC == 0) return (S)unpack32_raw(vw32, k, vh.bits, vmask) + vmin;
+    if (SRC == 1) return (S)unpack_at(vwords, k, vh.bits, vh.minv);
+    return (S)cur[k];
+  };
+  const uint32_t* const rw32 = rh.bits ? (const uint32_t*)rwords : (const uint32_t*)payload;
+  const uint32_t rmask = rh.bits >= 32u ? 0xffffffffu : ((1u << rh.bits) - 1u);
+  const uint32_t rmin = (uint32_t)rh.minv, rlast = nvals - 1u;
+  const uint32_t stage_s = smem_addr(stage);
+  S vcarry = (S)first;
+  uint32_t lcarry = 0;
+  for (uint32_t base = 0; base < nvals; base += 4u * kWarp) {
+    const uint32_t k0 = base + 4u * (uint32_t)lane;
+    S v[4];
+    if (has_delta) {
+      // value k = first + sum of the deltas before it (k = 0 .. count).  Deltas read past the last one (clamped
+      // index) only reach values past the last one, which no run stores.
+      S d[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[e] = (count != 0u) ? val(min(k0 + e, vlast)) : (S)0;
+      const S x2 = d[0] + d[1], x3 = x2 + d[2], tot = x3 + d[3];
+      const S incl = warp_incl_scan<S>(tot, lane);
+      const S ex = incl - tot + vcarry;
+      v[0] = ex; v[1] = ex + d[0]; v[2] = ex + x2; v[3] = ex + x3;
+      vcarry += __shfl_sync(kFull, incl, 31);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = val(min(k0 + e, vlast));
+    }
+    uint32_t len[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t l = unpack32_raw(rw32, min(k0 + e, rlast), rh.bits, rmask) + rmin;
+      len[e] = (k0 + e < nvals) ? min(l, cap + 1u) : 0u;   // (clipped: no wrap-around in the sums below)
+    }
+    const uint32_t ltot = len[0] + len[1] + len[2] + len[3];
+    const uint32_t lincl = warp_incl_scan<uint32_t>(ltot, lane);
+    const uint32_t pos0 = lincl - ltot + lcarry;
+    lcarry += __shfl_sync(kFull, lincl, 31);
+    if (lcarry > cap) return false;                   // every store below stays inside the staging buffer
+    // fill: the owner writes the first eight elements of each run (two at a time while any run of the warp is that
+    // long), the whole warp what a longer run has beyond
+    const uint32_t mx = max(max(len[0], len[1]), max(len[2], len[3]));
+    const unsigned m2 = __ballot_sync(kFull, mx > 2u);
+    uint32_t addr[4];
+    addr[0] = stage_s + (uint32_t)TS * pos0;
+    addr[1] = addr[0] + (uint32_t)TS * len[0];
+    addr[2] = addr[1] + (uint32_t)TS * len[1];
+    addr[3] = addr[2] + (uint32_t)TS * len[2];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (len[e] > 0u) sts_elem<TS, 0>(addr[e], v[e]);
+      if (len[e] > 1u) sts_elem<TS, 1>(addr[e], v[e]);
+    }
+    if (m2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (len[e] > 2u) sts_elem<TS, 2>(addr[e], v[e]);
+        if (len[e] > 3u) sts_elem<TS, 3>(addr[e], v[e]);
+      }
+      if (__any_sync(kFull, mx > 4u)) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (len[e] > 4u) sts_elem<TS, 4>(addr[e], v[e]);
+          if (len[e] > 5u) sts_elem<TS, 5>(addr[e], v[e]);
+          if (len[e] > 6u) sts_elem<TS, 6>(addr[e], v[e]);
+          if (len[e] > 7u) sts_elem<TS, 7>(addr[e], v[e]);
+        }
+        unsigned longm = __ballot_sync(kFull, mx > 8u);
+        while (longm) {
+          const int t = __ffs((int)longm) - 1;
+          longm &= longm - 1u;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t tl = __shfl_sync(kFull, len[e], t), ta = __shfl_sync(kFull, addr[e], t);
+            const S tv = __shfl_sync(kFull, v[e], t);
+            for (uint32_t j = 8u + (uint32_t)lane; j < tl; j += kWarp) sts_elem<TS, 0>(ta + (uint32_t)TS * j, tv);
+          }
+        }
+      }
+    }
+  }
+  const uint32_t total = lcarry;
+  if (total < nvals || total != n_out) return false;
+  __syncwarp();
+  // coalesced write-out
+  const uint32_t nbytes = total * (uint32_t)TS;
+  if ((((uintptr_t)out | stage_s) & 15u) == 0u) {
+    uint32_t j = 16u * (uint32_t)lane;
+    for (; j + 16u * kWarp + 16u <= nbytes; j += 32u * kWarp) {      // two vectors per lane in flight
+      const uint4 x0 = lds_v4(stage_s + j), x1 = lds_v4(stage_s + j + 16u * kWarp);
+      st_v4((uint4*)(out + j), x0);
+      st_v4((uint4*)(out + j + 16u * kWarp), x1);
+    }
+    for (; j + 16u <= nbytes; j += 16u * kWarp) st_v4((uint4*)(out + j), lds_v4(stage_s + j));
+    for (uint32_t t = (nbytes & ~15u) + (uint32_t)lane; t < nbytes; t += kWarp) out[t] = (uint8_t)lds_u8(stage_s + t);
+  } else {
+    T* const o = (T*)out;
+    for (uint32_t k = lane; k < total; k += kWarp) o[k] = stage[k];
+  }
+  return true;
+}
+
+// The first (up to) 256 bytes of a partition payload, one 32-bit word per lane and register; fields at uniform
+// offsets are broadcast with shuffles, anything beyond falls back to a global load.
+struct CascHead {
+  uint32_t w0, w1, n;
+  const uint8_t* base;
+  __device__ __forceinline__ CascHead(const uint8_t* __restrict__ payload, uint32_t payload_bytes, int lane) {
+    base = payload;
+    n = min(payload_bytes & ~3u, 256u);
+    const uint32_t* p32 = (const uint32_t*)payload;       // (8-byte aligned)
+    w0 = (4u * (uint32_t)lane + 4u <= n) ? __ldg(p32 + lane) : 0u;
+    w1 = (4u * (uint32_t)lane + 132u <= n) ? __ldg(p32 + 32 + lane) : 0u;
+  }
+  // off: the same in every lane, a multiple of 4, off + 4 <= payload bytes
+  __device__ __forceinline__ uint32_t u32(uint32_t off) const {
+    if (off + 4u <= n) {
+      const uint32_t a = __shfl_sync(kFull, w0, (int)((off >> 2) & 31u)), b = __shfl_sync(kFull, w1, (int)((off >> 2) & 31u));
+      return off < 128u ? a : b;
+    }
+    return __ldg((const uint32_t*)(base + off));
+  }
+  __device__ __forceinline__ uint64_t u64(uint32_t off) const { return (uint64_t)u32(off) | ((uint64_t)u32(off + 4u) << 32); }
+};
 
 // ---------------------------------------------------------------------------
 // Decode one partition with one warp.  `n_out` elements expected.
@@ -147,35 +321,45 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
   if (payload_bytes < firsts_bytes) return false;
   const uint64_t* firsts = (const uint64_t*)payload;
   const uint32_t* cin = (const uint32_t*)(payload + 8u * (uint32_t)D);   // element count entering delta i
+  // The first 256 bytes of the payload (delta bases, element counts, the stream headers of a compressed partition) come
+  // in with two independent coalesced loads; header fields are then picked with shuffles instead of one dependent
+  // global load after the other (a miss each: the walk below decides where the next header lies).
+  // (no per-layer arrays: a dynamically indexed local array lives in local memory; the header of run stream 0 --
+  // the only one the common configurations have -- stays in registers, deeper layers walk the headers again)
+  const CascHead head(payload, payload_bytes, lane);
   uint32_t off = firsts_bytes;
-  uint32_t run_off[8];
-  StreamHdr run_hdr[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < R) {
-      if (off + 16 > payload_bytes) return false;
-      const uint32_t* h = (const uint32_t*)(payload + off);
-      run_hdr[i].count = h[0]; run_hdr[i].bits = h[1];
-      run_hdr[i].minv = *(const uint64_t*)(payload + off + 8);
-      if (run_hdr[i].bits > 64 || run_hdr[i].count > cap) return false;
-      run_off[i] = off + 16;
-      off += stream_bytes(run_hdr[i].count, run_hdr[i].bits);
-      if (off > payload_bytes) return false;
-    }
+  StreamHdr rh0; rh0.count = 0; rh0.bits = 0; rh0.minv = 0;
+  uint32_t roff0 = 0;
+#pragma unroll 1
+  for (int i = 0; i < R; ++i) {
+    if (off + 16 > payload_bytes) return false;
+    const uint32_t cnt = head.u32(off), bits = head.u32(off + 4u);
+    if (bits > 64 || cnt > cap) return false;
+    if (i == 0) { rh0.count = cnt; rh0.bits = bits; rh0.minv = head.u64(off + 8u); roff0 = off + 16; }
+    off += stream_bytes(cnt, bits);
+    if (off > payload_bytes) return false;
   }
   if (off + 16 > payload_bytes) return false;
   StreamHdr vh;
-  {
-    const uint32_t* h = (const uint32_t*)(payload + off);
-    vh.count = h[0]; vh.bits = h[1];
-    vh.minv = *(const uint64_t*)(payload + off + 8);
-  }
+  vh.count = head.u32(off); vh.bits = head.u32(off + 4u);
+  vh.minv = head.u64(off + 8u);
   if (vh.bits > 64 || vh.count > cap) return false;
   const uint64_t* vwords = (const uint64_t*)(payload + off + 16);
   if (off + stream_bytes(vh.count, vh.bits) > payload_bytes) return false;
 
-  // unpack the final value stream into A
   uint32_t count = vh.count;
+  const int L = R > D ? R : D;
+  if (L == 1 && R == 1 && rh0.bits <= 32u) {
+    // the common configuration (one run-length layer, at most one delta layer): straight from the packed streams
+    const uint64_t* rwords = (const uint64_t*)(payload + roff0);
+    const bool hd = D > 0;
+    const uint64_t first = hd ? head.u64(0u) : 0ull;
+    const uint32_t c_in = hd ? head.u32(8u * (uint32_t)D) : 0u;
+    if (vh.bits <= 32u)
+      return casc_final_rle<TS, 0>(payload, vwords, vh, nullptr, count, hd, first, c_in, rh0, rwords, bufA, cap, out, n_out, lane);
+    return casc_final_rle<TS, 1>(payload, vwords, vh, nullptr, count, hd, first, c_in, rh0, rwords, bufA, cap, out, n_out, lane);
+  }
+  // unpack the final value stream into A
   if (vh.bits != 0u && vh.bits <= 32u) {
     const uint32_t* w32 = (const uint32_t*)vwords;
     const uint32_t mask = vh.bits == 32u ? 0xffffffffu : ((1u << vh.bits) - 1u);
@@ -185,8 +369,14 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
   }
   __syncwarp();
   T* cur = bufA;
-  const int L = R > D ? R : D;
   for (int i = L - 1; i >= 0; --i) {
+    if (i == 0 && R > 0 && rh0.bits <= 32u) {
+      // layer 0 with run-length encoding: fused delta + expansion from the buffer the layers above left
+      const uint64_t* rwords = (const uint64_t*)(payload + roff0);
+      const bool hd = D > 0;
+      return casc_final_rle<TS, 2>(payload, nullptr, vh, cur, count, hd, hd ? firsts[0] : 0ull, hd ? cin[0] : 0u, rh0, rwords,
+                                   cur == bufA ? bufB : bufA, cap, out, n_out, lane);
+    }
     if (i < D) {
       // undo delta i in place: cur[0..count) deltas -> cur[0..count] values.  cin == 0: the layer saw
       // an empty list.
@@ -227,12 +417,20 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
     }
     if (i < R) {
       // expand with runs_i: cur holds `count` values, runs_i holds `count` lengths
-      const StreamHdr rh = run_hdr[i];
+      // header of run stream i (validated by the walk above)
+      StreamHdr rh = rh0;
+      uint32_t roff = roff0;
+      for (int k = 1; k <= i; ++k) {
+        const uint32_t o = roff - 16u + stream_bytes(rh.count, rh.bits);
+        const uint32_t* h = (const uint32_t*)(payload + o);
+        rh.count = h[0]; rh.bits = h[1]; rh.minv = *(const uint64_t*)(payload + o + 8);
+        roff = o + 16u;
+      }
       if (rh.count != count) return false;
       const bool last = (i == 0);
       if (!last && !two_bufs) return false;                  // cannot happen: one buffer only when L == 1
       T* dst = last ? (T*)out : (cur == bufA ? bufB : bufA);
-      const uint64_t* rwords = (const uint64_t*)(payload + run_off[i]);
+      const uint64_t* rwords = (const uint64_t*)(payload + roff);
       // head flags: idx[start of run k] = k, zero elsewhere
       {
         uint32_t* z = (uint32_t*)idx;
@@ -317,13 +515,12 @@ struct CascHeader {
   int type, R, D, bp;
 };
 
-__device__ __forceinline__ bool casc_read_header(const uint8_t* in, size_t in_bytes, CascHeader& h) {
-  if (in_bytes < 20 || ((uintptr_t)in & 7)) return false;
-  const uint32_t* w = (const uint32_t*)in;
-  h.magic = w[0];
-  const uint32_t cfg = w[1];
+// the five header words -> fields + validation
+__device__ __forceinline__ bool casc_parse_header(uint32_t w0, uint32_t cfg, uint32_t w2, uint32_t w3, uint32_t w4,
+                                                  size_t in_bytes, CascHeader& h) {
+  h.magic = w0;
   h.type = cfg & 0xff; h.R = (cfg >> 8) & 0xff; h.D = (cfg >> 16) & 0xff; h.bp = (cfg >> 24) & 0xff;
-  h.uncompressed = w[2]; h.part_bytes = w[3]; h.num_parts = w[4];
+  h.uncompressed = w2; h.part_bytes = w3; h.num_parts = w4;
   if (h.magic != kCascMagic) return false;
   const uint32_t ts = casc_type_size(h.type);
   if (ts == 0 || h.R > 7 || h.D > 7) return false;
@@ -336,6 +533,12 @@ __device__ __forceinline__ bool casc_read_header(const uint8_t* in, size_t in_by
   return true;
 }
 
+__device__ __forceinline__ bool casc_read_header(const uint8_t* in, size_t in_bytes, CascHeader& h) {
+  if (in_bytes < 20 || ((uintptr_t)in & 7)) return false;
+  const uint32_t* w = (const uint32_t*)in;
+  return casc_parse_header(w[0], w[1], w[2], w[3], w[4], in_bytes, h);
+}
+
 __global__ void __launch_bounds__(kCascWarps * 32, 2)
 cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
                            const size_t* __restrict__ comp_bytes,
@@ -345,53 +548,79 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
                            nvcompStatus_t* statuses,
                            unsigned long long* ticket) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ unsigned long long s_chunk;
-  __shared__ int s_fail;
+  // Chunk indices and failure flags live in a ring of three slots: thread 0 draws tickets two chunks ahead while this
+  // one decodes (the atomic's latency is off the critical path), every warp knows the NEXT chunk at the top of the
+  // loop and sends its pointer and header lines on their way to L1 before the one barrier per chunk.
+  __shared__ unsigned long long s_chunk[3];
+  __shared__ int s_fail[3];
+  __shared__ const uint8_t* s_next_in;
+  __shared__ size_t s_next_bytes;
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
-  size_t static_next = blockIdx.x;
-  while (true) {
+  unsigned long long static_next = blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_chunk[0] = ticket ? atomicAdd(ticket, 1ull) : static_next;
+    s_chunk[1] = ticket ? atomicAdd(ticket, 1ull) : static_next + gridDim.x;
+    s_fail[0] = 0; s_fail[1] = 0;
+  }
+  static_next += 2ull * gridDim.x;
+  __syncthreads();
+  for (uint32_t cur = 0, nxt = 1, nn = 2;; ) {
+    const size_t c = (size_t)s_chunk[cur];
+    if (c >= batch) break;
+    const size_t cn = (size_t)s_chunk[nxt];
     if (threadIdx.x == 0) {
-      s_chunk = ticket ? atomicAdd(ticket, 1ull) : (unsigned long long)static_next;
-      s_fail = 0;
+      s_chunk[nn] = ticket ? atomicAdd(ticket, 1ull) : static_next;
+      s_fail[nn] = 0;
     }
     static_next += gridDim.x;
-    __syncthreads();
-    const size_t c = (size_t)s_chunk;
-    if (c >= batch) break;
+    if (threadIdx.x == 32) {                           // (parked in shared memory: no register lives across the decode)
+      s_next_in = cn < batch ? (const uint8_t*)comp_ptrs[cn] : nullptr;
+      s_next_bytes = cn < batch ? comp_bytes[cn] : 0;
+    }
     const uint8_t* in = (const uint8_t*)comp_ptrs[c];
     const size_t in_bytes = comp_bytes[c];
     uint8_t* out = (uint8_t*)out_ptrs[c];
     __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
     const size_t cap = out_caps[c];
+    // the chunk header and the first 27 partition offsets in one coalesced load (lane l holds word l of the chunk);
+    // fields are broadcast with shuffles: one miss instead of a header miss followed by an offset miss
     CascHeader h;
-    bool ok = casc_read_header(in, in_bytes, h);
+    bool ok = in_bytes >= 20 && ((uintptr_t)in & 7) == 0;
+    uint32_t cw = 0;
+    if (ok && 4u * (uint32_t)lane + 4u <= in_bytes) cw = __ldg((const uint32_t*)in + lane);
+    ok = ok && casc_parse_header(__shfl_sync(kFull, cw, 0), __shfl_sync(kFull, cw, 1), __shfl_sync(kFull, cw, 2),
+                                 __shfl_sync(kFull, cw, 3), __shfl_sync(kFull, cw, 4), in_bytes, h);
     if (ok && (h.uncompressed > cap || ((uintptr_t)out & (casc_type_size(h.type) - 1)))) ok = false;
     if (ok) {
       const uint32_t* part_off = (const uint32_t*)(in + 20);
       const uint32_t ts0 = casc_type_size(h.type);
       const uint32_t P = h.part_bytes;
       const bool two_bufs = (h.R > h.D ? h.R : h.D) > 1;
-      const uint32_t need = ((two_bufs ? 2u : 1u) * P + 2u * (P / ts0) + 4u + 15u) & ~15u;
-      int nw = (int)(kCascSmem / need);
-      if (nw > kCascWarps) nw = kCascWarps;
+      const uint32_t need = ((two_bufs ? 2u : 1u) * P + 2u * (P >> (__ffs((int)ts0) - 1)) + 4u + 15u) & ~15u;
+      const int nw = 16u * need <= kCascSmem ? kCascWarps : (int)(kCascSmem / need);   // (kCascWarps == 16)
       uint8_t* sm = smem + (size_t)w * need;
       if (w < nw) {
         for (uint32_t p = w; p < h.num_parts; p += nw) {
-          const uint32_t o0 = part_off[p], o1 = part_off[p + 1];
+          uint32_t o0, o1;
+          if (p + 6u < 32u) { o0 = __shfl_sync(kFull, cw, (int)(p + 5u)); o1 = __shfl_sync(kFull, cw, (int)(p + 6u)); }
+          else { o0 = part_off[p]; o1 = part_off[p + 1]; }
           bool pok = (o0 & 7) == 0 && o0 <= o1 && o1 <= in_bytes;
           if (pok) {
+            // the payload's cache lines start their way to L1 together: the header walk and the first unpack loads
+            // would otherwise fetch them one dependent miss after the other
+            for (uint32_t a = (o0 & ~127u) + 128u * (uint32_t)lane; a + 4u <= o1; a += 128u * kWarp)
+              touch_line(in + max(a, o0));
             const uint32_t begin = p * h.part_bytes;
-            const uint32_t ts = casc_type_size(h.type);
-            const uint32_t nbytes = min(h.part_bytes, h.uncompressed - h.uncompressed % ts - begin);
-            switch (ts) {
+            const uint32_t nbytes = min(h.part_bytes, h.uncompressed - h.uncompressed % ts0 - begin);
+            switch (ts0) {
               case 1: pok = casc_decode_part<1>(in + o0, o1 - o0, out + begin, nbytes, h.R, h.D, sm, P, two_bufs, lane); break;
               case 2: pok = casc_decode_part<2>(in + o0, o1 - o0, out + begin, nbytes / 2, h.R, h.D, sm, P, two_bufs, lane); break;
               case 4: pok = casc_decode_part<4>(in + o0, o1 - o0, out + begin, nbytes / 4, h.R, h.D, sm, P, two_bufs, lane); break;
               default: pok = casc_decode_part<8>(in + o0, o1 - o0, out + begin, nbytes / 8, h.R, h.D, sm, P, two_bufs, lane); break;
             }
           }
-          if (!pok && lane == 0) s_fail = 1;
+          if (!pok && lane == 0) s_fail[cur] = 1;
           __syncwarp();
         }
       }
@@ -399,17 +628,30 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
       const uint32_t tail = h.uncompressed % ts0;
       if (tail && w == 0) {
         const uint32_t to = part_off[h.num_parts];
-        if ((uint64_t)to + 8u > in_bytes) { if (lane == 0) s_fail = 1; }
+        if ((uint64_t)to + 8u > in_bytes) { if (lane == 0) s_fail[cur] = 1; }
         else if ((uint32_t)lane < tail) out[h.uncompressed - tail + lane] = in[to + lane];
       }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const bool good = ok && !s_fail;
-      if (actual_bytes) actual_bytes[c] = good ? (size_t)h.uncompressed : 0;
-      if (statuses) statuses[c] = good ? nvcompSuccess : nvcompErrorCannotDecompress;
+    // the next chunk: its sizes, header and partition offsets (the first lines of the stream) start towards L1 now
+    if (threadIdx.x == 32 && s_next_in) {
+      const uint8_t* const pn = s_next_in;
+      const size_t nb = s_next_bytes;
+      const size_t cn2 = (size_t)s_chunk[nxt];
+      touch_line(out_ptrs + cn2);
+      touch_line(out_caps + cn2);
+      if (((uintptr_t)pn & 3u) == 0u) {
+        if (nb >= 4) touch_line(pn);
+        if (nb >= 132) touch_line(pn + 128);
+      }
     }
-    __syncthreads();
+    __syncthreads();                                   // every partition of chunk c is done; the tickets are visible
+    if (threadIdx.x == 0) {
+      const bool good = ok && !s_fail[cur];
+      const size_t c2 = (size_t)s_chunk[cur];
+      if (actual_bytes) actual_bytes[c2] = good ? (size_t)h.uncompressed : 0;
+      if (statuses) statuses[c2] = good ? nvcompSuccess : nvcompErrorCannotDecompress;
+    }
+    const uint32_t t = cur; cur = nxt; nxt = nn; nn = t;
   }
 }
 

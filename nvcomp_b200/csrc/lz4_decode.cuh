@@ -171,6 +171,7 @@ struct Lz4Decode : Lz4Policy {
     ml += 4;
     if (off == 0 || (uint64_t)off > (uint64_t)s.op + ll) return -1;
     if ((uint64_t)ml > s.out_cap - s.op - ll) return -1;
+    lz_serial_lookahead<Lz4Policy>(s, ip, lane);
     lz_emit_literals(s, in + lit_at, ll, lane);
     lz_emit_match(s, off, ml, lane);
     s.ip = ip;

@@ -24,6 +24,11 @@
 
 #include "common.cuh"
 
+// counters for the host emulator's statistics build (tests/emu); nothing in the product
+#ifndef B200_LZ_STAT
+#define B200_LZ_STAT(slot, n) ((void)0)
+#endif
+
 namespace b200 {
 
 constexpr uint32_t kRingBytes = 4096;
@@ -234,6 +239,29 @@ __device__ __forceinline__ void lz_stage_issue(const LzState& s, uint32_t buf, c
   }
 }
 
+// Starts the copy of the block that begins at stream position next_ip into the idle buffer (at most one copy is in
+// flight: the caller checks s.pf_ip).  False when too few bytes are left for the block path.
+__device__ __forceinline__ bool lz_prefetch_block(LzState& s, uint32_t next_ip, int lane) {
+  const uint32_t nmis = (uint32_t)((uintptr_t)(s.in + next_ip) & 15u);
+  const uint32_t navail = s.in_n - next_ip + nmis;
+  if (navail < kSegBytes + kBlkPad) return false;
+  const uint32_t nnl = min((navail - kBlkPad) / kSegBytes, 32u);
+  lz_stage_issue(s, s.cur ^ 1u, s.in + next_ip - nmis, kSegBytes * nnl + kBlkPad, lane);
+  s.pf_ip = next_ip;
+  return true;
+}
+
+// A serial token knows where it ends before it moves its bytes: look at the token behind it then (the load and, when
+// the block path will take over there, the copy of that block overlap the byte moves) and leave the answer in s.next.
+template <class P>
+__device__ __forceinline__ void lz_serial_lookahead(LzState& s, uint32_t next_ip, int lane) {
+  s.next = kNextUnknown;
+  if (s.in_n - next_ip < kSegBytes + kBlkPad) return;
+  if (P::is_stop(s.in + next_ip)) { s.next = kNextSerial; return; }
+  s.next = kNextBlock;
+  if (s.pf_ip == kNoPrefetch) lz_prefetch_block(s, next_ip, lane);
+}
+
 // Returns the number of tokens retired (0: nothing done, the caller takes the serial path), -1 on a
 // malformed stream.
 template <class P>
@@ -288,6 +316,7 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
   {
     const uint32_t prev = my_ex - 4u;
     while (true) {
+      B200_LZ_STAT(7, 1);
       const uint32_t pe = __shfl_up_sync(kFull, e, 1);
       uint32_t ne = mis;
       if (ul != 0u) { ne = lds_u8(prev + lane_private(pe)); if (ne >= kSegBytes) ne = 0u; }
@@ -342,16 +371,7 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
   }
   // the size bytes are dead: prefetch the next block over them while this one executes (only when this block
   // ends at a token boundary the block path will continue from)
-  if (stop_lane == 32u) {
-    const uint32_t next_ip = s.ip + end_pos - mis;
-    const uint32_t nmis = (uint32_t)((uintptr_t)(s.in + next_ip) & 15u);
-    const uint32_t navail = s.in_n - next_ip + nmis;
-    if (navail >= kSegBytes + kBlkPad) {
-      const uint32_t nnl = min((navail - kBlkPad) / kSegBytes, 32u);
-      lz_stage_issue(s, s.cur ^ 1u, s.in + next_ip - nmis, kSegBytes * nnl + kBlkPad, lane);
-      s.pf_ip = next_ip;
-    }
-  }
+  if (stop_lane == 32u) lz_prefetch_block(s, s.ip + end_pos - mis, lane);
   __syncwarp();
 
   // ---- 4. execute ------------------------------------------------------------------------------
@@ -363,7 +383,10 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
   const uint8_t* const outa = s.out - s.align;
   const uint32_t cap_left0 = (uint32_t)min(s.out_cap - s.op, (uint64_t)0xffffffffu);
   uint32_t produced = 0;
+  B200_LZ_STAT(5, 1);
   for (uint32_t t0 = 0; t0 < N; t0 += 32u) {
+    B200_LZ_STAT(0, 1);
+    B200_LZ_STAT(1, min(N - t0, 32u));
     const bool valid = ul < N - t0;
     const uint32_t pos = lds_u16(rec + 2u * (t0 + (valid ? ul : 0u)));
     uint32_t L, M, off, lit_at;
@@ -432,6 +455,8 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
       unsigned dep = 0;
       const bool inwin = has && src_end > step_lo;
       if (__any_sync(kFull, inwin)) {
+        B200_LZ_STAT(3, 1);
+        B200_LZ_STAT(6, __popc(__ballot_sync(kFull, inwin)));
         const uint32_t key = valid ? dst : 0xffffffffu;
         const uint32_t qa = max(src, step_lo), qb = src_end - 1u;
         uint32_t ja = 0, jb = 0;
@@ -446,39 +471,54 @@ __device__ __forceinline__ int lz_block(LzState& s, int lane) {
       }
       const uint32_t sidx = src & kRingMask;
       const bool in_ring = src >= ring_from && sidx + M + 8u <= kRingBytes;
-      const bool far = src + M <= ring_from;                   // flushed long ago: read from global memory
+      // flushed long ago: read from the output buffer in global memory (whole words around the source: they must
+      // lie below this step's first byte, i.e. inside what the chunk has produced)
+      const bool far = src + M <= ring_from && (src & ~3u) + 12u <= step_lo;
       // groups of four bytes are loaded, then stored: needs off >= 4 and M >= 4 (shorter periods / copies
       // and anything that crosses the end of the ring take the byte loop)
       const bool simple = !wrap && off >= 4u && M >= 4u && (in_ring || far);
-      const bool c_r = has && simple && !far, c_g = has && simple && far, c_b = has && !simple;
+      const bool c_r0 = has && simple, c_r = c_r0 && !far, c_b = has && !simple;
       const uint32_t dp = rbase + (o_mat & kRingMask);
-      // sources flushed long ago are final: those matches run first, outside the rounds
-      if (__any_sync(kFull, c_g)) {
+      const uint32_t sa = rbase + (sidx & ~3u), sh = (src & 3u) * 8u;    // aligned words around the source
+      // sources flushed long ago are final: those matches run first, outside the rounds (their bytes may feed round 1)
+      const bool c_g = c_r0 && far;
+      const unsigned m_g = __ballot_sync(kFull, c_g);
+      if (m_g) {
         if (c_g) {
-          const uint8_t* const gp = outa + src;
-          for (uint32_t g = 0; g < M; g += 4u) {
-            const uint8_t* const g4 = gp + g;
-            const uint32_t d4 = dp + g;
-            uint32_t x1 = 0, x2 = 0, x3 = 0;
-            const uint32_t x0 = ldg_u8<0>(g4);
-            if (M > g + 1u) x1 = ldg_u8<1>(g4);
-            if (M > g + 2u) x2 = ldg_u8<2>(g4);
-            if (M > g + 3u) x3 = ldg_u8<3>(g4);
-            sts_u8<0>(d4, x0);
-            if (M > g + 1u) sts_u8<1>(d4, x1);
-            if (M > g + 2u) sts_u8<2>(d4, x2);
-            if (M > g + 3u) sts_u8<3>(d4, x3);
+          const uint8_t* const gp = outa + (src & ~3u);
+          const uint32_t w0 = ldg_u32<0>(gp), w1 = ldg_u32<4>(gp);
+          const uint32_t x = __funnelshift_r(w0, w1, sh);
+          sts_u8<0>(dp, x);
+          sts_u8<1>(dp, x >> 8);
+          sts_u8<2>(dp, x >> 16);
+          sts_u8<3>(dp, x >> 24);
+          if (M > 4u) {
+            const uint32_t y = __funnelshift_r(w1, ldg_u32<8>(gp), sh);
+            sts_u8<4>(dp, y);
+            if (M > 5u) sts_u8<5>(dp, y >> 8);
+            if (M > 6u) sts_u8<6>(dp, y >> 16);
+            if (M > 7u) sts_u8<7>(dp, y >> 24);
           }
         }
-        __syncwarp();                                           // their bytes may feed round 1
+        unsigned lg = __ballot_sync(kFull, c_g && M > 8u);      // bytes 8.. of a long far match: whole warp
+        while (lg) {
+          const int t = __ffs((int)lg) - 1;
+          lg &= lg - 1u;
+          const uint32_t tM = __shfl_sync(kFull, M, t), tsrc = __shfl_sync(kFull, src, t), tdp = __shfl_sync(kFull, dp, t);
+          const uint32_t j = 8u + ul;
+          if (j < tM) sts_u8(tdp + j, (uint32_t)outa[tsrc + j]);
+        }
+        __syncwarp();
       }
       const unsigned m_b = __ballot_sync(kFull, c_b);
       const unsigned m_4 = __ballot_sync(kFull, c_r && M > 4u);
       const unsigned m_8 = __ballot_sync(kFull, c_r && M > 8u);
       unsigned done = ~__ballot_sync(kFull, c_r || c_b);
       bool pend = c_r || c_b;
-      const uint32_t sa = rbase + (sidx & ~3u), sh = (sidx & 3u) * 8u;   // aligned words around the source
+      B200_LZ_STAT(4, __popc(__ballot_sync(kFull, has && far)));
+      B200_LZ_STAT(8, __popc(m_b));
       while (done != kFull) {
+        B200_LZ_STAT(2, 1);
         const bool ready = pend && (dep & ~done) == 0u;
         const unsigned rm = __ballot_sync(kFull, ready);
         const bool go = ready && c_r;
@@ -666,12 +706,13 @@ __device__ __forceinline__ bool lz_decode_loop(LzState& s, int lane) {
     // previous step does not already tell: a block that ended in a stop token is followed by that token, a block that
     // ran to its end is followed by the next (prefetched) block.
     const uint32_t next = s.next;
-    s.next = kNextUnknown;
+    s.next = kNextUnknown;                              // (the block path and serial tokens that look ahead set it)
     if (next != kNextSerial && s.in_n - s.ip >= kSegBytes + kBlkPad && (next == kNextBlock || !P::is_stop(s.in + s.ip))) {
       const int r = lz_block<P>(s, lane);
       if (r < 0) return false;
       if (r > 0) continue;
     }
+    B200_LZ_STAT(10, 1);
     const int r = P::serial_token(s, lane);
     if (r < 0) return false;
     lz_flush_blocks(s, lane);

@@ -77,6 +77,18 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
   asm volatile("ld.global.u8 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(O) : "memory");
   return v;
 }
+// touch one word of a cache line: the line travels to L1 while the warp goes on (the value is never used, so no
+// instruction waits for it)
+__device__ __forceinline__ void touch_line(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+}
+template <int O>
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.u32 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(O) : "memory");
+  return v;
+}
 
 // ---------------------------------------------------------------------------
 // TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: one thread stages a

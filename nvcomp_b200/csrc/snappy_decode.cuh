@@ -163,6 +163,7 @@ struct SnappyDecode : SnappyPolicy {
         len = v + 1;
       }
       if (len > in_n - ip || len > n_out - s.op) return -1;
+      lz_serial_lookahead<SnappyPolicy>(s, ip + len, lane);
       lz_emit_literals(s, in + ip, len, lane);
       s.ip = ip + len;
       return 1;
@@ -202,6 +203,7 @@ struct SnappyDecode : SnappyPolicy {
       ip += 4;
     }
     if (off == 0 || off > s.op || len > n_out - s.op) return -1;
+    lz_serial_lookahead<SnappyPolicy>(s, ip, lane);
     lz_emit_match(s, off, len, lane);
     s.ip = ip;
     return 1;

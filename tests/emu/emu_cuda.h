@@ -10,6 +10,9 @@
 #pragma once
 
 #include <cuda_runtime.h>   // vector types, __device__ / __forceinline__ macros (host flavour)
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -65,6 +65,14 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
   return p[O];
 }
 
+__device__ __forceinline__ void touch_line(const void* p) { emu::check_global(p, 4, false); }
+template <int O>
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p) {
+  if ((uintptr_t)(p + O) & 3u) emu::fail("misaligned ldg_u32 %p", (const void*)(p + O));
+  emu::check_global(p + O, 4, false);
+  uint32_t r; memcpy(&r, p + O, 4); return r;
+}
+
 // mbarrier + TMA bulk copy: the copy completes at once; the barrier is a phase counter in the 8 bytes it occupies
 // and a waiting lane yields to the other fibers until the phase it waits for has completed.
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t) { uint32_t z = 0; memcpy(emu::smem_ptr(mbar, 8), &z, 4); }

@@ -108,3 +108,27 @@ def test_emulated_decoder_rejects_malformed(emu, oracle):
         want = oracle.decompress(codec, garbage, 65536)
         got = emu.decode(codec, garbage, 65536, "block")
         assert (got is None) if want is None else (got == want)
+
+
+def test_emulated_decoder_token_chains(emu, oracle, liblz4):
+    """Records that repeat with a few mutated bytes: every match copies what the match before it copied, with
+    overlapping matches in between -- the longest dependency chains the block path's rounds meet."""
+    import pyarrow as pa
+    rng = np.random.default_rng(11)
+    for trial in range(10):
+        rec = int(rng.choice([3, 5, 7, 8, 9, 12, 16, 24]))
+        nrec = 65536 // rec
+        rows = np.tile(rng.integers(0, 256, rec, dtype=np.uint8), (nrec, 1))
+        pm = float(rng.choice([0.02, 0.1, 0.3]))
+        for i in range(1, nrec):
+            rows[i] = rows[i - 1]
+            m = rng.random(rec) < pm
+            rows[i][m] = rng.integers(0, 256, int(m.sum()), dtype=np.uint8)
+        data = rows.tobytes()
+        if trial % 3 == 0:
+            data = data[: int(rng.integers(100, len(data)))]
+        streams = [("lz4", liblz4.compress(data)), ("lz4", liblz4.compress(data, 12)), ("lz4", oracle.compress("lz4", data)),
+                   ("snappy", oracle.compress("snappy", data)), ("snappy", pa.Codec("snappy").compress(data).to_pybytes())]
+        for codec, comp in streams:
+            got = emu.decode(codec, comp, len(data), "block", in_mis=int(rng.integers(0, 16)), out_mis=int(rng.integers(0, 16)))
+            assert got == data, (trial, rec, pm, codec)

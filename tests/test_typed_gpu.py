@@ -46,7 +46,7 @@ def _roundtrip(codec, kind, raws, oracle, okw):
 
 
 @pytest.mark.parametrize("type_id", sorted(TS))
-@pytest.mark.parametrize("layers", [(0, 0, 1), (1, 0, 1), (1, 1, 1), (2, 1, 1), (2, 2, 0), (0, 1, 1), (3, 2, 1)])
+@pytest.mark.parametrize("layers", [(0, 0, 1), (1, 0, 1), (1, 1, 1), (2, 1, 1), (2, 2, 0), (0, 1, 1), (3, 2, 1), (1, 1, 0), (1, 0, 0)])
 def test_cascaded(oracle, type_id, layers):
     from nvcomp_b200._lib import CascadedOpts
     from nvcomp_b200.batched import Codec
