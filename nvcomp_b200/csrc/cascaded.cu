@@ -151,6 +151,25 @@ __device__ __forceinline__ uint32_t unpack32_raw(const uint32_t* __restrict__ w3
   return __funnelshift_r(lo, hi, s) & mask;
 }
 
+// raw values k0 .. k0+3 of such a stream (indices clamped to klast: what lies past it is never used).  Up to 8 bits per
+// value the four lie inside two consecutive words: two loads and four 64-bit shifts instead of eight loads.
+// nw32: 32-bit words the stream has.
+__device__ __forceinline__ void unpack32_x4(const uint32_t* __restrict__ w32, uint32_t k0, uint32_t klast, uint32_t bits,
+                                            uint32_t mask, uint32_t nw32, uint32_t r[4]) {
+  if (bits <= 8u) {
+    const uint32_t bitpos = min(k0, klast) * bits;
+    const uint32_t w = bitpos >> 5, s = bitpos & 31u;
+    const uint32_t lo = __ldg(w32 + w);
+    const uint32_t hi = (s + 4u * bits > 32u && w + 1u < nw32) ? __ldg(w32 + w + 1) : 0u;
+    const uint64_t x = ((uint64_t)hi << 32) | lo;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = (uint32_t)(x >> (s + (uint32_t)e * bits)) & mask;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = unpack32_raw(w32, min(k0 + e, klast), bits, mask);
+  }
+}
+
 template <int TS, int SRC>
 __device__ __forceinline__ bool casc_final_rle(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ vwords,
                                                const StreamHdr vh, const typename Elem<TS>::T* cur, uint32_t count,
@@ -180,6 +199,8 @@ __device__ __forceinline__ bool casc_final_rle(const uint8_t* __restrict__ paylo
   const uint32_t* const rw32 = rh.bits ? (const uint32_t*)rwords : (const uint32_t*)payload;
   const uint32_t rmask = rh.bits >= 32u ? 0xffffffffu : ((1u << rh.bits) - 1u);
   const uint32_t rmin = (uint32_t)rh.minv, rlast = nvals - 1u;
+  const uint32_t vnw32 = (uint32_t)(((uint64_t)count * vh.bits + 63u) >> 6) << 1;   // 32-bit words of the two streams
+  const uint32_t rnw32 = (uint32_t)(((uint64_t)nvals * rh.bits + 63u) >> 6) << 1;
   const uint32_t stage_s = smem_addr(stage);
   S vcarry = (S)first;
   uint32_t lcarry = 0;
@@ -190,23 +211,36 @@ __device__ __forceinline__ bool casc_final_rle(const uint8_t* __restrict__ paylo
       // value k = first + sum of the deltas before it (k = 0 .. count).  Deltas read past the last one (clamped
       // index) only reach values past the last one, which no run stores.
       S d[4];
+      if (SRC == 0) {
+        uint32_t r4[4] = {0u, 0u, 0u, 0u};
+        if (count != 0u) unpack32_x4(vw32, k0, vlast, vh.bits, vmask, vnw32, r4);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) d[e] = (count != 0u) ? val(min(k0 + e, vlast)) : (S)0;
+        for (int e = 0; e < 4; ++e) d[e] = (count != 0u) ? (S)r4[e] + vmin : (S)0;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = (count != 0u) ? val(min(k0 + e, vlast)) : (S)0;
+      }
       const S x2 = d[0] + d[1], x3 = x2 + d[2], tot = x3 + d[3];
       const S incl = warp_incl_scan<S>(tot, lane);
       const S ex = incl - tot + vcarry;
       v[0] = ex; v[1] = ex + d[0]; v[2] = ex + x2; v[3] = ex + x3;
       vcarry += __shfl_sync(kFull, incl, 31);
     } else {
+      if (SRC == 0) {
+        uint32_t r4[4];
+        unpack32_x4(vw32, k0, vlast, vh.bits, vmask, vnw32, r4);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = val(min(k0 + e, vlast));
+        for (int e = 0; e < 4; ++e) v[e] = (S)r4[e] + vmin;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = val(min(k0 + e, vlast));
+      }
     }
     uint32_t len[4];
+    unpack32_x4(rw32, k0, rlast, rh.bits, rmask, rnw32, len);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const uint32_t l = unpack32_raw(rw32, min(k0 + e, rlast), rh.bits, rmask) + rmin;
-      len[e] = (k0 + e < nvals) ? min(l, cap + 1u) : 0u;   // (clipped: no wrap-around in the sums below)
-    }
+    for (int e = 0; e < 4; ++e)
+      len[e] = (k0 + e < nvals) ? min(len[e] + rmin, cap + 1u) : 0u;   // (clipped: no wrap-around in the sums below)
     const uint32_t ltot = len[0] + len[1] + len[2] + len[3];
     const uint32_t lincl = warp_incl_scan<uint32_t>(ltot, lane);
     const uint32_t pos0 = lincl - ltot + lcarry;
@@ -275,25 +309,27 @@ __device__ __forceinline__ bool casc_final_rle(const uint8_t* __restrict__ paylo
   return true;
 }
 
-// The first (up to) 256 bytes of a partition payload, one 32-bit word per lane and register; fields at uniform
-// offsets are broadcast with shuffles, anything beyond falls back to a global load.
+// The first (up to) 256 bytes of a partition payload -- delta bases, element counts, the stream headers of a compressed
+// partition -- are fetched with two independent coalesced loads and parked in the warp's (still unused) staging
+// buffer; header fields are then shared-memory reads instead of one dependent global miss after the other (the walk
+// decides where the next header lies).  Offsets beyond the window fall back to a global load.
 struct CascHead {
-  uint32_t w0, w1, n;
+  uint32_t n, scratch;
   const uint8_t* base;
-  __device__ __forceinline__ CascHead(const uint8_t* __restrict__ payload, uint32_t payload_bytes, int lane) {
+  __device__ __forceinline__ CascHead(const uint8_t* __restrict__ payload, uint32_t payload_bytes, uint32_t scratch_s, int lane) {
     base = payload;
+    scratch = scratch_s;
     n = min(payload_bytes & ~3u, 256u);
     const uint32_t* p32 = (const uint32_t*)payload;       // (8-byte aligned)
-    w0 = (4u * (uint32_t)lane + 4u <= n) ? __ldg(p32 + lane) : 0u;
-    w1 = (4u * (uint32_t)lane + 132u <= n) ? __ldg(p32 + 32 + lane) : 0u;
+    const uint32_t w0 = (4u * (uint32_t)lane + 4u <= n) ? __ldg(p32 + lane) : 0u;
+    const uint32_t w1 = (4u * (uint32_t)lane + 132u <= n) ? __ldg(p32 + 32 + lane) : 0u;
+    sts_u32(scratch_s + 4u * (uint32_t)lane, w0);
+    sts_u32(scratch_s + 128u + 4u * (uint32_t)lane, w1);
+    __syncwarp();
   }
   // off: the same in every lane, a multiple of 4, off + 4 <= payload bytes
   __device__ __forceinline__ uint32_t u32(uint32_t off) const {
-    if (off + 4u <= n) {
-      const uint32_t a = __shfl_sync(kFull, w0, (int)((off >> 2) & 31u)), b = __shfl_sync(kFull, w1, (int)((off >> 2) & 31u));
-      return off < 128u ? a : b;
-    }
-    return __ldg((const uint32_t*)(base + off));
+    return (off + 4u <= n) ? lds_u32(scratch + off) : __ldg((const uint32_t*)(base + off));
   }
   __device__ __forceinline__ uint64_t u64(uint32_t off) const { return (uint64_t)u32(off) | ((uint64_t)u32(off + 4u) << 32); }
 };
@@ -326,7 +362,8 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
   // global load after the other (a miss each: the walk below decides where the next header lies).
   // (no per-layer arrays: a dynamically indexed local array lives in local memory; the header of run stream 0 --
   // the only one the common configurations have -- stays in registers, deeper layers walk the headers again)
-  const CascHead head(payload, payload_bytes, lane);
+  const CascHead head(payload, payload_bytes, smem_addr(sm), lane);
+  // (every field is in a register before anything is written to the staging buffer: __syncwarp below)
   uint32_t off = firsts_bytes;
   StreamHdr rh0; rh0.count = 0; rh0.bits = 0; rh0.minv = 0;
   uint32_t roff0 = 0;
@@ -347,14 +384,18 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
   const uint64_t* vwords = (const uint64_t*)(payload + off + 16);
   if (off + stream_bytes(vh.count, vh.bits) > payload_bytes) return false;
 
+  const uint64_t first0 = D > 0 ? head.u64(0u) : 0ull;          // base and element count of delta layer 0
+  const uint32_t cin0 = D > 0 ? head.u32(8u * (uint32_t)D) : 0u;
+  __syncwarp();                                                // the header window is dead: the buffer may be written
+
   uint32_t count = vh.count;
   const int L = R > D ? R : D;
   if (L == 1 && R == 1 && rh0.bits <= 32u) {
     // the common configuration (one run-length layer, at most one delta layer): straight from the packed streams
     const uint64_t* rwords = (const uint64_t*)(payload + roff0);
     const bool hd = D > 0;
-    const uint64_t first = hd ? head.u64(0u) : 0ull;
-    const uint32_t c_in = hd ? head.u32(8u * (uint32_t)D) : 0u;
+    const uint64_t first = first0;
+    const uint32_t c_in = cin0;
     if (vh.bits <= 32u)
       return casc_final_rle<TS, 0>(payload, vwords, vh, nullptr, count, hd, first, c_in, rh0, rwords, bufA, cap, out, n_out, lane);
     return casc_final_rle<TS, 1>(payload, vwords, vh, nullptr, count, hd, first, c_in, rh0, rwords, bufA, cap, out, n_out, lane);
@@ -374,7 +415,7 @@ __device__ bool casc_decode_part(const uint8_t* __restrict__ payload, uint32_t p
       // layer 0 with run-length encoding: fused delta + expansion from the buffer the layers above left
       const uint64_t* rwords = (const uint64_t*)(payload + roff0);
       const bool hd = D > 0;
-      return casc_final_rle<TS, 2>(payload, nullptr, vh, cur, count, hd, hd ? firsts[0] : 0ull, hd ? cin[0] : 0u, rh0, rwords,
+      return casc_final_rle<TS, 2>(payload, nullptr, vh, cur, count, hd, first0, cin0, rh0, rwords,
                                    cur == bufA ? bufB : bufA, cap, out, n_out, lane);
     }
     if (i < D) {
@@ -548,15 +589,20 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
                            nvcompStatus_t* statuses,
                            unsigned long long* ticket) {
   extern __shared__ __align__(16) uint8_t smem[];
-  // Chunk indices and failure flags live in a ring of three slots: thread 0 draws tickets two chunks ahead while this
-  // one decodes (the atomic's latency is off the critical path), every warp knows the NEXT chunk at the top of the
-  // loop and sends its pointer and header lines on their way to L1 before the one barrier per chunk.
+  // Chunk indices and failure flags live in a ring of three slots: thread 0 draws the ticket two chunks ahead while
+  // this one decodes and parks it just before the one barrier per chunk, so no warp ever waits for the atomic.
+  // The descriptor of a chunk (stream pointer and size, output pointer and capacity) is fetched one chunk ahead by
+  // four lanes of warp 1 -- loads issued at the top of the loop, parked in shared memory before the barrier -- so the
+  // sixteen warps do not start every chunk with a miss on the four descriptor arrays.
   __shared__ unsigned long long s_chunk[3];
+  __shared__ unsigned long long s_desc[3][4];
   __shared__ int s_fail[3];
-  __shared__ const uint8_t* s_next_in;
-  __shared__ size_t s_next_bytes;
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
+  auto load_desc = [&](size_t c, int which) -> unsigned long long {
+    return which == 0 ? (unsigned long long)comp_ptrs[c] : which == 1 ? (unsigned long long)comp_bytes[c]
+         : which == 2 ? (unsigned long long)out_ptrs[c] : (unsigned long long)out_caps[c];
+  };
   unsigned long long static_next = blockIdx.x;
   if (threadIdx.x == 0) {
     s_chunk[0] = ticket ? atomicAdd(ticket, 1ull) : static_next;
@@ -565,24 +611,23 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
   }
   static_next += 2ull * gridDim.x;
   __syncthreads();
+  if (w == 1 && lane < 4 && s_chunk[0] < batch) s_desc[0][lane] = load_desc((size_t)s_chunk[0], lane);
+  __syncthreads();
   for (uint32_t cur = 0, nxt = 1, nn = 2;; ) {
     const size_t c = (size_t)s_chunk[cur];
     if (c >= batch) break;
-    const size_t cn = (size_t)s_chunk[nxt];
-    if (threadIdx.x == 0) {
-      s_chunk[nn] = ticket ? atomicAdd(ticket, 1ull) : static_next;
-      s_fail[nn] = 0;
-    }
+    // the ticket two chunks ahead is drawn now and parked before the barrier: warp 0 does not wait for the atomic
+    unsigned long long drawn = static_next;
+    if (threadIdx.x == 0 && ticket) drawn = atomicAdd(ticket, 1ull);
     static_next += gridDim.x;
-    if (threadIdx.x == 32) {                           // (parked in shared memory: no register lives across the decode)
-      s_next_in = cn < batch ? (const uint8_t*)comp_ptrs[cn] : nullptr;
-      s_next_bytes = cn < batch ? comp_bytes[cn] : 0;
-    }
-    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
-    const size_t in_bytes = comp_bytes[c];
-    uint8_t* out = (uint8_t*)out_ptrs[c];
+    unsigned long long pre = 0;                        // the next chunk's descriptor word of this lane (warp 1)
+    const bool pre_lane = w == 1 && lane < 4 && s_chunk[nxt] < batch;
+    if (pre_lane) pre = load_desc((size_t)s_chunk[nxt], lane);
+    const uint8_t* in = (const uint8_t*)s_desc[cur][0];
+    const size_t in_bytes = (size_t)s_desc[cur][1];
+    uint8_t* out = (uint8_t*)s_desc[cur][2];
     __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
-    const size_t cap = out_caps[c];
+    const size_t cap = (size_t)s_desc[cur][3];
     // the chunk header and the first 27 partition offsets in one coalesced load (lane l holds word l of the chunk);
     // fields are broadcast with shuffles: one miss instead of a header miss followed by an offset miss
     CascHeader h;
@@ -607,10 +652,6 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
           else { o0 = part_off[p]; o1 = part_off[p + 1]; }
           bool pok = (o0 & 7) == 0 && o0 <= o1 && o1 <= in_bytes;
           if (pok) {
-            // the payload's cache lines start their way to L1 together: the header walk and the first unpack loads
-            // would otherwise fetch them one dependent miss after the other
-            for (uint32_t a = (o0 & ~127u) + 128u * (uint32_t)lane; a + 4u <= o1; a += 128u * kWarp)
-              touch_line(in + max(a, o0));
             const uint32_t begin = p * h.part_bytes;
             const uint32_t nbytes = min(h.part_bytes, h.uncompressed - h.uncompressed % ts0 - begin);
             switch (ts0) {
@@ -632,18 +673,8 @@ cascaded_decompress_kernel(const void* const* __restrict__ comp_ptrs,
         else if ((uint32_t)lane < tail) out[h.uncompressed - tail + lane] = in[to + lane];
       }
     }
-    // the next chunk: its sizes, header and partition offsets (the first lines of the stream) start towards L1 now
-    if (threadIdx.x == 32 && s_next_in) {
-      const uint8_t* const pn = s_next_in;
-      const size_t nb = s_next_bytes;
-      const size_t cn2 = (size_t)s_chunk[nxt];
-      touch_line(out_ptrs + cn2);
-      touch_line(out_caps + cn2);
-      if (((uintptr_t)pn & 3u) == 0u) {
-        if (nb >= 4) touch_line(pn);
-        if (nb >= 132) touch_line(pn + 128);
-      }
-    }
+    if (threadIdx.x == 0) { s_chunk[nn] = drawn; s_fail[nn] = 0; }
+    if (pre_lane) s_desc[nxt][lane] = pre;
     __syncthreads();                                   // every partition of chunk c is done; the tickets are visible
     if (threadIdx.x == 0) {
       const bool good = ok && !s_fail[cur];
