@@ -13,11 +13,20 @@
 
 namespace b200 {
 
-constexpr int kLzDecWarps = 4;
+#ifndef LZ_DEC_WARPS
+#define LZ_DEC_WARPS 4
+#endif
+constexpr int kLzDecWarps = LZ_DEC_WARPS;
 // dense kernel: 7 CTAs x 4 warps per SM -- shared memory (ring + staged block + token records per warp) sets the limit
-constexpr int kLzDecCtasPerSm = 7;
+#ifndef LZ_DEC_CTAS
+#define LZ_DEC_CTAS 7
+#endif
+constexpr int kLzDecCtasPerSm = LZ_DEC_CTAS;
 // light kernel: no shared memory, 10 CTAs x 4 warps per SM (long copies want many warps in flight)
-constexpr int kLzLightCtasPerSm = 10;
+#ifndef LZ_LIGHT_CTAS
+#define LZ_LIGHT_CTAS 10
+#endif
+constexpr int kLzLightCtasPerSm = LZ_LIGHT_CTAS;
 
 __global__ void __launch_bounds__(kLzDecWarps * 32, kLzLightCtasPerSm)
 snappy_decompress_light_kernel(const void* const* __restrict__ comp_ptrs,
