@@ -59,6 +59,23 @@ __device__ __forceinline__ bool snappy_decode_chunk(const uint8_t* __restrict__ 
           const uint32_t nf = (uint32_t)__ffs((int)~m) - 1u;     // leading run of continuations (< 10)
           ml += __reduce_add_sync(kFull, ul < nf ? (e0 >> 2) + 1u : 0u);
           used += 3u * nf;
+          // every element the window shows continues the run and more input follows: look at the next 32 bytes (ten
+          // whole elements) as long as that holds -- a run longer than the ~600 bytes one window spells stays here
+          // instead of taking the read-back copy below for its tail
+          if (nf != 0u && used + 3u > 32u) {
+            while (ip + used + 32u <= in_n) {
+              const uint32_t b2 = in[ip + used + ul];
+              const uint32_t q = 3u * ul;
+              const uint32_t f0 = __shfl_sync(kFull, b2, (int)(q & 31u)), f1 = __shfl_sync(kFull, b2, (int)((q + 1u) & 31u)),
+                             f2 = __shfl_sync(kFull, b2, (int)((q + 2u) & 31u));
+              const bool same2 = ul < 10u && (f0 & 3u) == 2u && (f1 | (f2 << 8)) == off;
+              const uint32_t nf2 = (uint32_t)__ffs((int)~__ballot_sync(kFull, same2)) - 1u;      // <= 10
+              if (nf2 == 0u) break;
+              ml += __reduce_add_sync(kFull, ul < nf2 ? (f0 >> 2) + 1u : 0u);
+              used += 3u * nf2;
+              if (nf2 < 10u || ml > 0x10000u) break;
+            }
+          }
           if (ll <= n_out - op && ml <= n_out - op - ll) {
             if (ul - 1u < ll) out[op + ul - 1u] = (uint8_t)b;    // literals: window lanes 1..ll
             lz_expand_period_from_window(out + op + ll, ml, off, b, 1u + ll - off, ul);

@@ -132,3 +132,24 @@ def test_emulated_decoder_token_chains(emu, oracle, liblz4):
         for codec, comp in streams:
             got = emu.decode(codec, comp, len(data), "block", in_mis=int(rng.integers(0, 16)), out_mis=int(rng.integers(0, 16)))
             assert got == data, (trial, rec, pm, codec)
+
+
+def test_emulated_direct_decoder_long_runs(emu, oracle):
+    """Typed run-length data with runs longer than one 32-byte window of copy elements spells (Snappy: 64 bytes per
+    element): the direct decoder keeps merging continuation elements window after window."""
+    import pyarrow as pa
+    rng = np.random.default_rng(3)
+    for trial in range(8):
+        per = int(rng.choice([1, 2, 4, 8]))
+        parts, total = [], 0
+        while total < 65536:
+            run = rng.integers(0, 256, per, dtype=np.uint8).tobytes() * int(rng.integers(1, 1300))
+            parts.append(run)
+            total += len(run)
+        data = b"".join(parts)[:65536]
+        for comp in (oracle.compress("snappy", data), pa.Codec("snappy").compress(data).to_pybytes()):
+            for mode in ("direct", "adaptive"):
+                got = emu.decode("snappy", comp, len(data), mode, in_mis=int(rng.integers(0, 16)), out_mis=int(rng.integers(0, 16)))
+                assert got == data, (trial, per, mode)
+        comp = oracle.compress("lz4", data)
+        assert emu.decode("lz4", comp, len(data), "direct") == data

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Kernel-iteration run on a GPU box: LZ + typed parity tests, per-dataset throughput of the LZ and Cascaded decoders,
-# one full ncu capture.   bash tools/gpu_iter2.sh <tag> [ncu_codec] [ncu_dataset] [ncu_kernel_regex]
+# one full ncu capture.   bash tools/gpu_iter.sh <tag> [ncu_codec] [ncu_dataset] [ncu_kernel_regex]
 set -u
 TAG=${1:-it}
 NC=${2:-cascaded}
