@@ -36,9 +36,6 @@ lz4_size_kernel(const void* const* __restrict__ comp_ptrs, const size_t* __restr
 }
 
 
-#ifndef LZ_STEAL
-#define LZ_STEAL 1
-#endif
 #ifndef LZ_DEC_WARPS
 #define LZ_DEC_WARPS 4
 #endif
@@ -114,25 +111,6 @@ lz4_decompress_v2_kernel(const void* const* __restrict__ comp_ptrs,
     }
     __syncwarp();
   }
-  // the dense list is exhausted: instead of idling (this CTA holds its registers and shared memory until its last
-  // warp is done) take light chunks the light kernel has not reached yet (lz_sched.cuh, "work stealing")
-#if LZ_STEAL
-  for (size_t c = sched.steal(lane); c < batch; c = sched.steal(lane)) {
-    const size_t in_n64 = comp_bytes[c];
-    const uint64_t cap = (uint64_t)out_caps[c];
-    const uint8_t* in = (const uint8_t*)comp_ptrs[c];
-    uint8_t* out = (uint8_t*)out_ptrs[c];
-    __builtin_assume(__isGlobal(in)); __builtin_assume(__isGlobal(out));
-    uint32_t produced = 0;
-    bool ok = in_n64 <= 0xffffffffull;
-    if (ok) ok = lz4_decode_chunk_direct(in, (uint32_t)in_n64, out, cap, &produced, lane);
-    if (lane == 0) {
-      if (actual_bytes) actual_bytes[c] = ok ? (size_t)produced : 0;
-      if (statuses) statuses[c] = ok ? nvcompSuccess : nvcompErrorCannotDecompress;
-    }
-    __syncwarp();
-  }
-#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -291,7 +269,7 @@ nvcompStatus_t nvcompBatchedLZ4DecompressAsync(
   if (!comp_ptrs || !comp_bytes || !out_caps || !out_ptrs) return nvcompErrorInvalidValue;
   const LzLists lists = lz_lists_in(temp, temp_bytes, batch);
   if (lists.ctr) {
-    B200_CUDA_TRY(cudaMemsetAsync(lists.ctr, 0, kLzCounters * sizeof(unsigned long long), stream));
+    B200_CUDA_TRY(cudaMemsetAsync(lists.ctr, 0, 4 * sizeof(unsigned long long), stream));
     lz_classify_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, stream>>>(comp_bytes, out_caps, batch, lists);
   }
   // dense kernel on the caller's stream, light kernel beside it (see StreamFork): both are ordered after the ticket

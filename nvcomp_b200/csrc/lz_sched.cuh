@@ -7,12 +7,6 @@
 // caller's workspace; each kernel's persistent warps then pull from their own list with an atomic ticket, so a
 // kernel whose list is empty retires at once instead of walking the whole batch.  Without a workspace (temp ==
 // nullptr is legal for these codecs) both kernels stride over all chunks and skip the other kernel's.
-//
-// Work stealing: the dense kernel's warps hold the SM's registers and shared memory until the last dense chunk is
-// done, and a batch with fewer dense chunks than a few waves of warps (5000 of the 10000 chunks of a mixed table
-// against 4144 resident warps) leaves most of them idle in the last wave while the light kernel waits for room.  A
-// dense warp whose list is exhausted therefore takes light chunks from the END of the light list (direct decoder,
-// same code as the light kernel); every light chunk is claimed with one atomic exchange by whoever gets to it first.
 #pragma once
 
 #include "common.cuh"
@@ -23,23 +17,19 @@ __device__ __forceinline__ bool lz_chunk_is_light(uint64_t cap, uint64_t in_n) {
   return cap >= 4ull * in_n || in_n + (cap >> 6) >= cap;
 }
 
-// workspace: kSchedBytes of counters | u32 light[batch] | u32 dense[batch] | u32 claim[batch]
+// workspace: kSchedBytes of counters | u32 light[batch] | u32 dense[batch]
 struct LzLists {
-  unsigned long long* ctr;      // [0] light ticket, [1] dense ticket, [2] number of light chunks, [3] of dense chunks,
-                                // [4] light chunks offered to the dense kernel's idle warps (from the end of the list)
+  unsigned long long* ctr;      // [0] light ticket, [1] dense ticket, [2] number of light chunks, [3] of dense chunks
   uint32_t* light;
   uint32_t* dense;
-  uint32_t* claim;              // claim[t] != 0: entry t of the light list is taken
 };
-constexpr int kLzCounters = 5;
-inline size_t lz_decode_temp_bytes(size_t batch) { return kSchedBytes + ((12 * batch + 255) & ~(size_t)255); }
+inline size_t lz_decode_temp_bytes(size_t batch) { return kSchedBytes + ((8 * batch + 255) & ~(size_t)255); }
 inline LzLists lz_lists_in(void* temp, size_t temp_bytes, size_t batch) {
-  LzLists l{nullptr, nullptr, nullptr, nullptr};
+  LzLists l{nullptr, nullptr, nullptr};
   if (temp && temp_bytes >= lz_decode_temp_bytes(batch) && batch <= 0xffffffffull) {
     l.ctr = (unsigned long long*)temp;
     l.light = (uint32_t*)((uint8_t*)temp + kSchedBytes);
     l.dense = l.light + batch;
-    l.claim = l.dense + batch;
   }
   return l;
 }
@@ -50,7 +40,6 @@ lz_classify_kernel(const size_t* __restrict__ comp_bytes, const size_t* __restri
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = lane_id();
   const bool in_range = i < batch;
-  if (in_range) l.claim[i] = 0u;
   const bool light = in_range && lz_chunk_is_light((uint64_t)out_caps[i], (uint64_t)comp_bytes[i]);
   const bool dense = in_range && !light;
   // one atomic per warp and list: the warp's chunks are appended in lane order
@@ -71,10 +60,6 @@ lz_classify_kernel(const size_t* __restrict__ comp_bytes, const size_t* __restri
 // filtered by class.
 struct LzWork {
   const uint32_t* list;
-  uint32_t* claim;              // light list only
-  const uint32_t* steal_list;   // dense kernel: the light list, its length and the steal counter
-  unsigned long long steal_count;
-  unsigned long long* steal_ctr;
   unsigned long long count;
   unsigned long long* ticket;
   const size_t* comp_bytes;
@@ -83,9 +68,7 @@ struct LzWork {
   bool want_light, first;
   __device__ __forceinline__ LzWork(const LzLists& l, bool light, const size_t* cb, const size_t* oc, size_t n,
                                     size_t warp_global, size_t warps_total)
-      : list(l.ctr ? (light ? l.light : l.dense) : nullptr), claim(l.ctr ? l.claim : nullptr),
-        steal_list(l.ctr && !light ? l.light : nullptr), steal_count(l.ctr && !light ? l.ctr[2] : 0),
-        steal_ctr(l.ctr ? l.ctr + 4 : nullptr), count(l.ctr ? l.ctr[light ? 2 : 3] : 0),
+      : list(l.ctr ? (light ? l.light : l.dense) : nullptr), count(l.ctr ? l.ctr[light ? 2 : 3] : 0),
         ticket(l.ctr ? l.ctr + (light ? 0 : 1) : nullptr), comp_bytes(cb), out_caps(oc), batch(n),
         static_next(warp_global), static_stride(warps_total), want_light(light), first(true) {}
   // next chunk of this warp, or batch when there is none
@@ -94,23 +77,16 @@ struct LzWork {
       // The first chunk of every warp is static (list entry = global warp index), the rest come from the ticket.  With
       // fewer chunks than resident warps this packs the work into whole CTAs -- the CTAs behind them retire at once --
       // instead of leaving every resident CTA half idle while it still holds its shared memory and registers.
-      while (true) {
-        unsigned long long t;
-        if (first) {
-          first = false;
-          t = static_next;
-        } else {
-          t = 0;
-          if (lane == 0) t = atomicAdd(ticket, 1ull);
-          t = __shfl_sync(kFull, t, 0) + static_stride;
-        }
-        if (t >= count) return batch;
-        if (!want_light) return (size_t)list[t];
-        // a light chunk may have been taken by an idle warp of the dense kernel
-        unsigned taken = 0;
-        if (lane == 0) taken = atomicExch(claim + t, 1u);
-        if (__shfl_sync(kFull, taken, 0) == 0u) return (size_t)list[t];
+      unsigned long long t;
+      if (first) {
+        first = false;
+        t = static_next;
+      } else {
+        t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1ull);
+        t = __shfl_sync(kFull, t, 0) + static_stride;
       }
+      return t < count ? (size_t)list[t] : batch;
     }
     while (static_next < batch) {
       const size_t c = static_next;
@@ -118,20 +94,6 @@ struct LzWork {
       if (lz_chunk_is_light((uint64_t)out_caps[c], (uint64_t)comp_bytes[c]) == want_light) return c;
     }
     return batch;
-  }
-  // dense kernel, own list exhausted: an unclaimed light chunk from the end of the light list, or batch
-  __device__ __forceinline__ size_t steal(int lane) {
-    if (!steal_list) return batch;
-    while (true) {
-      unsigned long long s = 0;
-      if (lane == 0) s = atomicAdd(steal_ctr, 1ull);
-      s = __shfl_sync(kFull, s, 0);
-      if (s >= steal_count) return batch;
-      const unsigned long long t = steal_count - 1ull - s;
-      unsigned taken = 0;
-      if (lane == 0) taken = atomicExch(claim + t, 1u);
-      if (__shfl_sync(kFull, taken, 0) == 0u) return (size_t)steal_list[t];
-    }
   }
 };
 
