@@ -592,7 +592,10 @@ def run_gpu(args):
                         "what": "the decode launches alone, inputs resident (no distribution), max over ranks"},
         "e2e": e2e,
         "e2e_device_consumer": e2e_dev,
-        "gpu_launches": 2 * args.steps if kind in ("lz4", "snappy") else args.steps,
+        # kernels of this library inside the timed region, per rank: an LZ DecompressAsync is three launches
+        # (classification, dense decoder, light decoder), the others one; the N > 1 job decodes in NSLICES calls per
+        # step (rank 0: one call on the slab it holds)
+        "gpu_launches": (3 if kind in ("lz4", "snappy") else 1) * args.steps * (DistributedJob.NSLICES if world > 1 else 1),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic,
                      "traffic_source": traffic_src or "not captured for this workload",
