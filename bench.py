@@ -18,6 +18,7 @@ Prints ONE JSON line (rank 0):
   per_dataset    the survey's own cfg2 definitions: (i) reference gen_data(3), (ii) price-walk float32 column
   foreign_streams  the same workload compressed on the HOST by an independent codec (pyarrow-snappy / liblz4 default
                  and HC-12) and decoded on the GPU, parity-gated
+  cfg1           (--codec lz4) BASELINE configs[0]: 16 x 64 KB LZ4 round trip, latency in us next to liblz4 on one core
   cpu_baseline   liblz4's LZ4_decompress_safe (LZ4) / the oracle port on this box's host cores, median and best
   cfg5           (N > 1, or --cfg5) BASELINE configs[4]: LZ4, 80,000 x 64 KB chunks in total, strong scaling
 """
@@ -472,6 +473,67 @@ def measure(kind, dataset, n, rank, world, args, sampler=None):
     return res
 
 
+def cfg1_latency():
+    """BASELINE configs[0] (reference benchmark_lz4_synth.cpp:64-72): LZ4 round trip of 1 MB of synthetic int32
+    run-length data as 16 x 64 KB chunks on one GPU -- a latency figure (one launch over 16 chunks is far from filling
+    the GPU), next to liblz4 on one host core over the same chunks."""
+    import torch
+    n = 16
+    w = Workload("lz4", "runlength_i32", n)
+    sh = torch.cuda.current_stream().cuda_stream
+    codec = w.codec
+    ctb = codec.compress_get_temp_size(n, CHUNK)
+    ctemp = torch.empty(max(ctb, 1), dtype=torch.uint8, device=w.dense.device)
+    from nvcomp_b200.batched import empty_batch
+    max_out = codec.compress_get_max_output_chunk_size(CHUNK)
+    cout = empty_batch(n, max_out)
+    csz = torch.zeros(n, dtype=torch.int64, device=w.dense.device)
+
+    def timed(fn, reps=60, warm=5):
+        for _ in range(warm):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        t = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+        return t[len(t) // 2], t[0]
+
+    c_med, c_best = timed(lambda: codec.compress_async(w.inp.ptrs.data_ptr(), w.inp.sizes.data_ptr(), CHUNK, n,
+                                                       ctemp.data_ptr(), ctb, cout.ptrs.data_ptr(), csz.data_ptr(), sh))
+    d_med, d_best = timed(lambda: w.launch(sh))
+    w.check()
+    out = {"workload": "BASELINE configs[0]: LZ4 round trip, 16 x 64 KB int32 run-length chunks (1 MB), one launch each way",
+           "ratio": round(w.total / w.comp_total, 2),
+           "gpu_compress_us": round(c_med, 1), "gpu_decompress_us": round(d_med, 1),
+           "gpu_decompress_best_us": round(d_best, 1),
+           "gpu_decompress_GBps": round(w.total / d_med / 1e3, 2),
+           "what": "CUDA events around one CompressAsync / DecompressAsync over the 16 chunks, median of 60 (device-resident)"}
+    try:
+        lz4 = C.CDLL("liblz4.so.1")
+        lz4.LZ4_compress_default.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        lz4.LZ4_decompress_safe.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        cap = CHUNK + CHUNK // 255 + 64
+        raws = [w.data[i].tobytes() for i in range(n)]
+        bufs = [C.create_string_buffer(cap) for _ in range(n)]
+        outb = C.create_string_buffer(CHUNK)
+        ct, dt = [], []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            sizes = [lz4.LZ4_compress_default(r, b, CHUNK, cap) for r, b in zip(raws, bufs)]
+            t1 = time.perf_counter()
+            for b, sz in zip(bufs, sizes):
+                lz4.LZ4_decompress_safe(b, outb, sz, CHUNK)
+            t2 = time.perf_counter()
+            ct.append((t1 - t0) * 1e6); dt.append((t2 - t1) * 1e6)
+        out.update({"liblz4_compress_us": round(sorted(ct)[10], 1), "liblz4_decompress_us": round(sorted(dt)[10], 1),
+                    "liblz4": "liblz4.so.1 LZ4_compress_default / LZ4_decompress_safe, one host thread, the 16 chunks in turn "
+                              "(includes the ctypes call overhead, ~1 us per chunk), median of 20"})
+    except OSError:
+        out["liblz4"] = "liblz4.so.1 not found on this box"
+    return out
+
+
 def foreign_streams(kind, base: Workload, args, peak):
     """The same chunks compressed on the HOST by an independent codec, decoded on the GPU (bit-exact gate)."""
     from concurrent.futures import ThreadPoolExecutor
@@ -619,6 +681,8 @@ def run_gpu(args):
                 del wd
             line["per_dataset"] = per
             line["foreign_streams"] = foreign_streams(kind, w, args, peak)
+            if kind == "lz4":
+                line["cfg1"] = cfg1_latency()
         if not args.no_cpu:
             sample = min(n, args.cpu_chunks)
             host = w.dense[: int(w.c_offs[sample - 1] + w.c_sizes[sample - 1])].cpu().numpy()
