@@ -3,7 +3,8 @@
 // One warp owns one chunk.  On tabular data a 64 KB chunk holds 10-15 thousand *short* tokens
 // (4-8 output bytes each), so throughput is bounded by warp-instructions per token, not bytes.
 //
-//  * BLOCK PATH (lz_block): 1 KB of compressed input is staged in shared memory; every lane finds the
+//  * BLOCK PATH (lz_block): 1 KB of compressed input is staged in shared memory by a TMA bulk copy (the next
+//    block is prefetched while this one executes); every lane finds the
 //    token chain through its own 32-byte segment (exit table computed right to left, entries resolved
 //    across lanes), the ~350-500 tokens of the block are listed in stream order and executed 32 per
 //    step, one token per lane: literals from the staged block, matches in dependency rounds.
@@ -14,10 +15,12 @@
 //  * SERIAL PATH (P::serial_token + lz_emit_*): tokens with length-extension bytes / long lengths are
 //    parsed once by the whole warp; up to 192 bytes they are executed inside the ring, longer runs go
 //    straight to global memory as 16-byte vectors (periodic runs are built in registers, no
-//    store->load round trip) and the ring restarts empty behind them.
-//  * Chunks that compressed >= 4x never enter this machinery: the callers (lz4_decode.cuh /
-//    snappy_decode.cuh) decode them with the direct global-memory token loop, and the kernels hand
-//    dense chunks out first (two-pass ticket).
+//    store->load round trip) and the ring restarts empty behind them.  A serial token looks at the token
+//    behind it before it moves its bytes (lz_serial_lookahead): the block copy that follows is in flight
+//    during the move and the driver does not peek at global memory in steady state.
+//  * Chunks that compressed >= 4x (and incompressible ones) never enter this machinery: a classification
+//    pass puts them on the light kernel's list (lz_sched.cuh), which decodes them with the direct
+//    global-memory token loop of lz4_decode.cuh / snappy_decode.cuh.
 //
 // Format specifics (token grammar, stream end, size limits) come from a policy.
 #pragma once
@@ -189,9 +192,9 @@ struct SnappyPolicy {
 // ---------------------------------------------------------------------------
 // Block path.  One call parses up to kBlkBytes of compressed input and executes its tokens.
 //
-//   1. stage   lane l loads its 32-byte segment of the block (16-byte aligned base), stores it to
-//              shared memory together with the token size every byte would have as a tag (sizes4);
-//              kBlkPad more bytes cover tokens that start in the last segment.
+//   1. stage   the block (16-byte aligned base, kBlkPad more bytes for tokens that start in the last
+//              segment) arrives by cp.async.bulk; lane l reads its 32-byte segment and writes the token
+//              size every byte would have as a tag (sizes4) into the other block buffer.
 //   2. chain   every lane computes, right to left over its own 32 size bytes (in registers, fully
 //              unrolled), where a token chain entering its segment at byte p leaves it: a 32-entry
 //              exit table per lane.  The true entry of every segment is the fixpoint of
@@ -203,7 +206,8 @@ struct SnappyPolicy {
 //   4. execute 32 consecutive tokens per step, one per lane: a warp scan of the output lengths
 //              places them, literals come from the staged block, matches run in dependency rounds:
 //              a match runs as soon as the tokens of this step that produce its source bytes have
-//              run (sources below the step are final).
+//              run (sources below the step are final; sources flushed long ago are read from global
+//              memory as aligned words before the rounds).
 // ---------------------------------------------------------------------------
 constexpr uint32_t kSegBytes = 32;
 constexpr uint32_t kBlkBytes = 32 * kSegBytes;
