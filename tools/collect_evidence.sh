@@ -56,7 +56,10 @@ timeout 500 ncu --set full --clock-control none --import-source on -k regex:snap
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:lz4_decompress_light -c 1 -f \
   -o $O/${TAG}_lz4_runlength_i32 python tools/quick_bench.py --codecs lz4 --datasets runlength_i32 --iters 2 --no-verify \
   > $O/${TAG}_ncu_lz4_rl.log 2>&1
-ls -la $O/${TAG}_snappy_price_walk.ncu-rep $O/${TAG}_lz4_runlength_i32.ncu-rep 2>&1 | cut -c1-120
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:snappy_decompress_light -c 1 -f \
+  -o $O/${TAG}_snappy_runlength_i32 python tools/quick_bench.py --codecs snappy --datasets runlength_i32 --iters 2 --no-verify \
+  > $O/${TAG}_ncu_snappy_rl.log 2>&1
+ls -la $O/${TAG}_snappy_price_walk.ncu-rep $O/${TAG}_lz4_runlength_i32.ncu-rep $O/${TAG}_snappy_runlength_i32.ncu-rep 2>&1 | cut -c1-120
 
 echo "== compute-sanitizer memcheck"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_fuzz_gpu.py -x -q -m gpu \

@@ -86,7 +86,8 @@ def main():
                 if len(r) > h.index("Metric Value") and r[h.index("Metric Name")].startswith("dram__bytes"):
                     traffic[f"{c}:{ds}"] += int(to_bytes(r[h.index("Metric Value")].replace(",", ""), r[h.index("Metric Unit")]))
     for name, title in (("snappy_price_walk", "snappy dense block decoder, 10000 x 64 KB chunks (tabular_f32:0, price-walk column)"),
-                        ("lz4_runlength_i32", "lz4 light (direct) kernel, 10000 x 64 KB chunks (runlength_i32)")):
+                        ("lz4_runlength_i32", "lz4 light (direct) kernel, 10000 x 64 KB chunks (runlength_i32)"),
+                        ("snappy_runlength_i32", "snappy light (direct) kernel, 10000 x 64 KB chunks (runlength_i32)")):
         rep = os.path.join(SRC, f"{TAG}_{name}.ncu-rep")
         if os.path.exists(rep):
             md = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, f"round {TAG[1:]} — {title}"],
